@@ -1,0 +1,788 @@
+// api.cu - the C ABI of libinb200 (include/inb200.h): argument checking, the plan / workspace,
+// and the network drivers that walk the L x K flow steps inside the library.
+#include "../../include/inb200.h"
+#include "glow.cuh"
+
+#include <cstring>
+#include <memory>
+#include <algorithm>
+#include <stdexcept>
+
+namespace inb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error{code, buf};
+}
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return INB_OK;
+  } catch (const Error& e) {
+    set_last_error(e.msg);
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("internal error: ") + e.what());
+    return INB_ERR_INVALID;
+  } catch (...) {
+    set_last_error("unknown internal error");
+    return INB_ERR_INVALID;
+  }
+}
+
+// stream-ordered temporary arena for the layer-level entry points
+struct TempArena {
+  Arena ar;
+  cudaStream_t st;
+  TempArena(cudaStream_t s) : st(s) {}
+  void reserve(size_t bytes) {
+    void* p = nullptr;
+    INB_CUDA(cudaMallocAsync(&p, bytes + 512, st));
+    ar.base = (char*)p;
+    ar.cap = bytes + 512;
+    ar.off = 0;
+    ar.dry = false;
+  }
+  ~TempArena() {
+    if (ar.base) cudaFreeAsync(ar.base, st);
+  }
+};
+// run `body` once dry to size the workspace, then for real
+template <class F>
+static void with_temp_arena(cudaStream_t st, int prec, F&& body) {
+  Arena dry;
+  dry.dry = true;
+  Ctx dc{st, &dry, prec};
+  body(dc);
+  TempArena t(st);
+  t.reserve(dry.peak);
+  Ctx c{st, &t.ar, prec};
+  body(c);
+}
+
+}  // namespace inb
+
+using namespace inb;
+
+// ====================================================================== plan
+struct ScaleInfo {
+  Geo g;        // geometry of the flow steps at this scale
+  int C;        // channels during the flow steps
+  int Ccond;    // condition channels at this scale
+  int has_split;
+  int kc;       // channels that continue after the split (== C when no split)
+};
+
+struct inb_plan {
+  inb_glow_desc d;
+  bool cond;
+  std::vector<ScaleInfo> sc;
+  Geo g0;  // input geometry
+  Arena ar;
+  size_t persist = 0;  // bytes at the start of the arena that survive calls (logdet accumulator)
+  size_t need = 0;     // workspace bytes (sizing pass at plan creation)
+  double* ld = nullptr;
+};
+
+static int an_index(const inb_plan* p, int i, int j, int which) { return 2 * (i * p->d.K + j) + which; }
+static int cl_index(const inb_plan* p, int i, int j, int which) {
+  return 2 * p->d.L * p->d.K + (p->cond ? 2 : 0) + 8 * (i * p->d.K + j) + which;
+}
+static int anc_index(const inb_plan* p, int which) { return 2 * p->d.L * p->d.K + which; }
+
+static void plan_scales(inb_plan* p) {
+  const inb_glow_desc& d = p->d;
+  p->g0 = make_geo(d.ndims, d.nx, d.ny, d.nz);
+  Geo g = p->g0;
+  int c = d.n_in, cc = d.n_cond;
+  const int f = 1 << d.ndims;
+  for (int i = 0; i < d.L; ++i) {
+    ScaleInfo s{};
+    if (d.split_scales) {
+      INB_CHECK(!(g.W % 2) && !(g.H % 2) && (g.nd == 2 || !(g.D % 2)),
+                "Input dimensions must be multiple of 2");  // dimensionality_operations.jl:82-84
+      c *= f;
+      cc *= f;
+      g = half_geo(g);
+    }
+    s.g = g;
+    s.C = c;
+    s.Ccond = cc;
+    // invertible_network_glow.jl:120 (i < L || i == 1) ; conditional_glow.jl:122 (i < L)
+    s.has_split = d.split_scales && (i < d.L - 1 || (!p->cond && i == 0));
+    s.kc = s.has_split ? split_k(c) : c;
+    INB_CHECK(c >= 2, "a coupling layer needs at least 2 channels (scale %d has %d)", i + 1, c);
+    p->sc.push_back(s);
+    if (d.split_scales && i < d.L - 1) c = c / 2;  // ctor :100
+    if (s.has_split) INB_CHECK(s.kc == c || i == d.L - 1, "internal: split bookkeeping");
+  }
+}
+
+static FlowShape flow_shape(const inb_plan* p, int i, int B) {
+  const ScaleInfo& s = p->sc[i];
+  FlowShape f{};
+  f.g = s.g;
+  f.B = B;
+  f.C = s.C;
+  f.ccond = p->cond ? s.Ccond : 0;
+  f.nh = p->d.n_hidden;
+  f.k1 = p->d.k1;
+  f.k2 = p->d.k2;
+  f.low = p->d.sig_low;
+  f.high = p->d.sig_high;
+  f.logdet = p->d.logdet;
+  f.freeze = p->d.freeze_conv;
+  return f;
+}
+static FlowParams flow_params(const inb_plan* p, int i, int j, float* const* prm) {
+  FlowParams fp{};
+  if (!prm) return fp;
+  fp.s = prm[an_index(p, i, j, 0)];
+  fp.b = prm[an_index(p, i, j, 1)];
+  fp.v1 = prm[cl_index(p, i, j, 0)];
+  fp.v2 = prm[cl_index(p, i, j, 1)];
+  fp.v3 = prm[cl_index(p, i, j, 2)];
+  fp.rb = RBParams{prm[cl_index(p, i, j, 3)], prm[cl_index(p, i, j, 4)], prm[cl_index(p, i, j, 5)],
+                   prm[cl_index(p, i, j, 6)], prm[cl_index(p, i, j, 7)]};
+  return fp;
+}
+static FlowGrads flow_grads(const inb_plan* p, int i, int j, float* const* gr) {
+  FlowGrads fg{};
+  if (!gr) return fg;
+  fg.s = gr[an_index(p, i, j, 0)];
+  fg.b = gr[an_index(p, i, j, 1)];
+  fg.v1 = gr[cl_index(p, i, j, 0)];
+  fg.v2 = gr[cl_index(p, i, j, 1)];
+  fg.v3 = gr[cl_index(p, i, j, 2)];
+  fg.rb = RBGrads{gr[cl_index(p, i, j, 3)], gr[cl_index(p, i, j, 4)], gr[cl_index(p, i, j, 5)],
+                  gr[cl_index(p, i, j, 6)], gr[cl_index(p, i, j, 7)]};
+  return fg;
+}
+
+// element offset of latent block `i` in the flat Z vector and of the tail (block index L)
+static long long z_offset(const inb_plan* p, int B, int upto) {
+  long long off = 0;
+  for (int i = 0; i < upto && i < (int)p->sc.size(); ++i) {
+    const ScaleInfo& s = p->sc[i];
+    if (s.has_split) off += (long long)B * (s.C - s.kc) * s.g.px;
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------- drivers
+// `prm` null in the sizing pass (pointers are never dereferenced on the host).
+static void drive_forward(inb_plan* p, Ctx& c, int B, const float* X, const float* Cnd, float* const* prm,
+                          float* Z, float* ZC, float* logdet, int init) {
+  const inb_glow_desc& d = p->d;
+  const long long tot = (long long)d.n_in * p->g0.px;  // elements per sample
+  size_t m = c.ar->mark();
+  float* buf[2] = {c.ar->f32((size_t)B * tot), c.ar->f32((size_t)B * tot)};
+  float* cbuf[2] = {nullptr, nullptr};
+  const long long ctot = (long long)d.n_cond * p->g0.px;
+  if (p->cond) {
+    cbuf[0] = c.ar->f32((size_t)B * ctot);
+    cbuf[1] = c.ar->f32((size_t)B * ctot);
+  }
+  if (d.logdet) op_zero(c, p->ld, sizeof(double));
+  View cur = view(const_cast<float*>(X), tot);
+  int which = 0;  // buffer that is free to write
+  View cond = view(nullptr, 0);
+  int cwhich = 0;
+  if (p->cond) {
+    // C = AN_C.forward(C), logdet = false                        conditional_glow.jl:111
+    float* s = prm ? prm[anc_index(p, 0)] : nullptr;
+    float* b = prm ? prm[anc_index(p, 1)] : nullptr;
+    View cin = view(const_cast<float*>(Cnd), ctot);
+    if (init) op_actnorm_init(c, p->g0.px, B, d.n_cond, cin, s, b);
+    bool last = !d.split_scales;
+    View cout = view(last ? ZC : cbuf[0], ctot);
+    op_an_hh_fwd(c, p->g0.px, B, d.n_cond, cin, cout, s, b, nullptr, nullptr, nullptr, nullptr);
+    cond = cout;
+    cwhich = 1;
+  }
+  Geo g = p->g0;
+  int chan = d.n_in, cchan = d.n_cond;
+  for (int i = 0; i < d.L; ++i) {
+    const ScaleInfo& s = p->sc[i];
+    if (d.split_scales) {
+      View out = view(buf[which], (long long)s.C * s.g.px);
+      op_squeeze(c, g, B, chan, cur, out);  // :114
+      cur = out;
+      which ^= 1;
+      if (p->cond) {
+        bool last = (i == d.L - 1);
+        View co = view(last ? ZC : cbuf[cwhich], (long long)s.Ccond * s.g.px);
+        op_squeeze(c, g, B, cchan, cond, co);  // conditional_glow.jl:116
+        cond = co;
+        cwhich ^= 1;
+      }
+      g = s.g;
+      chan = s.C;
+      cchan = s.Ccond;
+    }
+    FlowShape f = flow_shape(p, i, B);
+    for (int j = 0; j < d.K; ++j) {
+      FlowParams fp = flow_params(p, i, j, prm);
+      if (init) op_actnorm_init(c, s.g.px, B, s.C, cur, const_cast<float*>(fp.s), const_cast<float*>(fp.b));
+      View out = view(buf[which], (long long)s.C * s.g.px);
+      flow_forward(c, f, cur, out, cond, fp, p->ld);  // :116-118
+      cur = out;
+      which ^= 1;
+    }
+    if (s.has_split) {  // :120-124: X = first part, Z = second part
+      long long off = z_offset(p, B, i);
+      int zc = s.C - s.kc;
+      op_copy(c, s.g.px, B, zc, sub(cur, s.kc, s.g.px), view(Z + off, (long long)zc * s.g.px));
+      chan = s.kc;
+    }
+  }
+  // tail: cat_states (:126) / plain output
+  {
+    const ScaleInfo& s = p->sc[d.L - 1];
+    long long off = z_offset(p, B, d.L);
+    op_copy(c, s.g.px, B, chan, cur, view(Z + off, (long long)chan * s.g.px));
+  }
+  if (d.logdet && logdet) op_ld_finish(c, p->ld, logdet);
+  c.ar->release(m);
+}
+
+// inverse (grads == false) and backward (grads == true) share the reverse sweep
+static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* dZ, const float* Z,
+                          const float* ZC, float* const* prm, float* const* gr, float* dX, float* X,
+                          float* dC) {
+  const inb_glow_desc& d = p->d;
+  const long long tot = (long long)d.n_in * p->g0.px;
+  const long long ctot = (long long)d.n_cond * p->g0.px;
+  size_t m = c.ar->mark();
+  float* yb[2] = {c.ar->f32((size_t)B * tot), c.ar->f32((size_t)B * tot)};
+  float* db[2] = {nullptr, nullptr};
+  if (grads) {
+    db[0] = c.ar->f32((size_t)B * tot);
+    db[1] = c.ar->f32((size_t)B * tot);
+  }
+  float* cb[2] = {nullptr, nullptr};
+  float* dcb[2] = {nullptr, nullptr};
+  if (p->cond) {
+    cb[0] = c.ar->f32((size_t)B * ctot);
+    cb[1] = c.ar->f32((size_t)B * ctot);
+    if (grads) {
+      dcb[0] = c.ar->f32((size_t)B * ctot);
+      dcb[1] = c.ar->f32((size_t)B * ctot);
+    }
+  }
+  int which = 0, cwhich = 0;
+  // tail block -> first kc channels of the scale-L buffer
+  const ScaleInfo& sl = p->sc[d.L - 1];
+  {
+    long long off = z_offset(p, B, d.L);
+    View dst = view(yb[which], (long long)sl.C * sl.g.px);
+    op_copy(c, sl.g.px, B, sl.kc, view(const_cast<float*>(Z) + off, (long long)sl.kc * sl.g.px), dst);
+    if (grads) {
+      View ddst = view(db[which], (long long)sl.C * sl.g.px);
+      op_copy(c, sl.g.px, B, sl.kc, view(const_cast<float*>(dZ) + off, (long long)sl.kc * sl.g.px), ddst);
+    }
+  }
+  View cond = view(const_cast<float*>(ZC), p->cond ? (long long)sl.Ccond * sl.g.px : 0);
+  View dcond = view(nullptr, 0);
+  if (p->cond && grads) {
+    dcond = view(dcb[cwhich], cond.bs);
+    op_zero(c, dcond.p, (size_t)B * ctot * sizeof(float));  // conditional_glow.jl:160
+  }
+  for (int i = d.L - 1; i >= 0; --i) {
+    const ScaleInfo& s = p->sc[i];
+    const long long bs = (long long)s.C * s.g.px;
+    View y = view(yb[which], bs);
+    View dy = view(grads ? db[which] : nullptr, bs);
+    if (s.has_split) {  // :168-169 tensor_cat with the saved latent
+      long long off = z_offset(p, B, i);
+      int zc = s.C - s.kc;
+      op_copy(c, s.g.px, B, zc, view(const_cast<float*>(Z) + off, (long long)zc * s.g.px), sub(y, s.kc, s.g.px));
+      if (grads)
+        op_copy(c, s.g.px, B, zc, view(const_cast<float*>(dZ) + off, (long long)zc * s.g.px), sub(dy, s.kc, s.g.px));
+    }
+    FlowShape f = flow_shape(p, i, B);
+    for (int j = d.K - 1; j >= 0; --j) {
+      FlowParams fp = flow_params(p, i, j, prm);
+      View xo = y, dxo = dy;
+      const bool final_step = (i == 0 && j == 0 && !d.split_scales);
+      if (final_step) {  // write straight into the caller's buffers
+        xo = view(X, bs);
+        dxo = view(dX, bs);
+      }
+      if (grads) {
+        FlowGrads fg = flow_grads(p, i, j, gr);
+        flow_backward(c, f, dy, y, dxo, xo, cond, dcond, fp, fg);  // :173-174
+      } else {
+        flow_inverse(c, f, y, xo, cond, fp);  // :139-140
+      }
+    }
+    if (d.split_scales) {  // :186-187 unsqueeze
+      Geo gout = (i == 0) ? p->g0 : make_geo(d.ndims, s.g.W * 2, s.g.H * 2, s.g.D * 2);
+      int cout = s.C >> d.ndims;
+      long long obs = (i == 0) ? tot : (long long)p->sc[i - 1].C * p->sc[i - 1].g.px;
+      float* xdst = (i == 0) ? X : yb[which ^ 1];
+      op_unsqueeze(c, gout, B, cout, y, view(xdst, obs));
+      if (grads) {
+        float* ddst = (i == 0) ? dX : db[which ^ 1];
+        op_unsqueeze(c, gout, B, cout, dy, view(ddst, obs));
+      }
+      which ^= 1;
+      if (p->cond) {
+        int ccout = s.Ccond >> d.ndims;
+        long long cbs = (long long)ccout * gout.px;
+        View cn = view(cb[cwhich], cbs);
+        op_unsqueeze(c, gout, B, ccout, cond, cn);  // conditional_glow.jl:171
+        if (grads) {
+          View dn = view(dcb[cwhich ^ 1], cbs);
+          op_unsqueeze(c, gout, B, ccout, dcond, dn);  // :172
+          dcond = dn;
+        }
+        cond = cn;
+        cwhich ^= 1;
+      }
+    }
+  }
+  if (p->cond && grads) {
+    // dC, C = AN_C.backward(dC, C)                               conditional_glow.jl:179
+    float* s = prm ? prm[anc_index(p, 0)] : nullptr;
+    float* b = prm ? prm[anc_index(p, 1)] : nullptr;
+    size_t m2 = c.ar->mark();
+    double* dsdb = c.ar->f64(2 * (size_t)d.n_cond);
+    op_zero(c, dsdb, 2 * d.n_cond * sizeof(double));
+    // cond lives in cb[] or is the caller's ZC (no split scales): never write into ZC
+    float* scratch = c.ar->f32((size_t)B * ctot);
+    op_hh_an_bwd(c, p->g0.px, B, d.n_cond, dcond, cond, view(dC, ctot), view(scratch, ctot), s, b, nullptr,
+                 nullptr, nullptr, nullptr, dsdb);
+    op_an_grad_finish(c, d.n_cond, p->g0.px, dsdb, s, 0, gr ? gr[anc_index(p, 0)] : nullptr,
+                      gr ? gr[anc_index(p, 1)] : nullptr);
+    c.ar->release(m2);
+  }
+  c.ar->release(m);
+}
+
+static void check_desc(const inb_glow_desc* d) {
+  INB_CHECK(d != nullptr, "null descriptor");
+  INB_CHECK(d->ndims == 2 || d->ndims == 3, "ndims must be 2 or 3 (got %d)", d->ndims);
+  INB_CHECK(d->nx > 0 && d->ny > 0 && (d->ndims == 2 || d->nz > 0), "spatial sizes must be positive");
+  INB_CHECK(d->n_in >= 1 && d->n_hidden >= 1 && d->L >= 1 && d->K >= 1 && d->batch >= 1,
+            "n_in, n_hidden, L, K, batch must be >= 1");
+  INB_CHECK(d->n_cond >= 0, "n_cond must be >= 0");
+  INB_CHECK((d->k1 == 1 || d->k1 == 3) && (d->k2 == 1 || d->k2 == 3),
+            "supported ResidualBlock kernel sizes are 1 and 3 (got k1=%d k2=%d)", d->k1, d->k2);
+  INB_CHECK(d->p1 == (d->k1 - 1) / 2 && d->p2 == (d->k2 - 1) / 2,
+            "only 'same' padding is supported (p = (k-1)/2; got p1=%d p2=%d)", d->p1, d->p2);
+  INB_CHECK(d->precision >= 0 && d->precision <= 2, "unknown precision mode %d", d->precision);
+  INB_CHECK(d->sig_high > d->sig_low, "sigmoid high must exceed low");
+}
+
+extern "C" {
+
+const char* inb_last_error(void) { return g_last_error.c_str(); }
+int inb_version(void) { return 100; }
+int inb_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return 0;
+  int dev = 0;
+  cudaDeviceProp pr;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&pr, dev) != cudaSuccess) return 0;
+  return pr.major == 10 ? 1 : 0;
+}
+
+int inb_glow_plan_create(const inb_glow_desc* desc, inb_plan** out) {
+  return guarded([&] {
+    INB_CHECK(out != nullptr, "null output");
+    *out = nullptr;
+    check_desc(desc);
+    std::unique_ptr<inb_plan> p(new inb_plan());
+    p->d = *desc;
+    if (p->d.n_in == 1 && p->d.n_cond == 0) p->d.split_scales = 1;  // invertible_network_glow.jl:79
+    if (p->d.ndims == 2) p->d.nz = 1;
+    p->cond = p->d.n_cond > 0;
+    if (p->cond) p->d.logdet = 1;  // the conditional network always carries logdet (:107-130)
+    plan_scales(p.get());
+    // sizing pass
+    Arena dry;
+    dry.dry = true;
+    dry.alloc_bytes(256);  // persistent: logdet accumulator
+    size_t persist = dry.off;
+    Ctx dc{nullptr, &dry, p->d.precision};
+    const int B = p->d.batch;
+    drive_forward(p.get(), dc, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1);
+    drive_reverse(p.get(), dc, B, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    // the device block is allocated on first use, so a plan can be created (and its parameter /
+    // latent bookkeeping queried) on a host without a GPU
+    p->need = dry.peak + 1024;
+    (void)persist;
+    *out = p.release();
+  });
+}
+
+int inb_glow_plan_destroy(inb_plan* p) {
+  return guarded([&] {
+    if (!p) return;
+    if (p->ar.base) cudaFree(p->ar.base);
+    delete p;
+  });
+}
+
+int inb_glow_num_params(const inb_plan* p) {
+  if (!p) return -1;
+  return 10 * p->d.L * p->d.K + (p->cond ? 2 : 0);
+}
+
+int inb_glow_param_numel(const inb_plan* p, int index, long long* numel) {
+  return guarded([&] {
+    INB_CHECK(p && numel, "null argument");
+    const int LK = p->d.L * p->d.K;
+    INB_CHECK(index >= 0 && index < inb_glow_num_params(p), "parameter index %d out of range", index);
+    if (index < 2 * LK) {
+      *numel = p->sc[(index / 2) / p->d.K].C;
+      return;
+    }
+    index -= 2 * LK;
+    if (p->cond) {
+      if (index < 2) { *numel = p->d.n_cond; return; }
+      index -= 2;
+    }
+    const int layer = index / 8, which = index % 8;
+    const ScaleInfo& s = p->sc[layer / p->d.K];
+    const int C1 = split_k(s.C), nh = p->d.n_hidden;
+    const int Cin = s.C - C1 + (p->cond ? s.Ccond : 0), Cout = 2 * C1;
+    long long t1 = 1, t2 = 1;
+    for (int a = 0; a < p->d.ndims; ++a) { t1 *= p->d.k1; t2 *= p->d.k2; }
+    switch (which) {
+      case 0: case 1: case 2: *numel = s.C; break;
+      case 3: *numel = t1 * Cin * nh; break;
+      case 4: *numel = t2 * nh * nh; break;
+      case 5: *numel = t1 * Cout * nh; break;
+      default: *numel = nh; break;
+    }
+  });
+}
+
+long long inb_glow_workspace_bytes(const inb_plan* p) { return p ? (long long)p->need : -1; }
+
+int inb_glow_zdims(const inb_plan* p, int batch, int scale, int* dims5) {
+  if (!p || !dims5 || scale < 0 || scale >= p->d.L) return -1;
+  const ScaleInfo& s = p->sc[scale];
+  int zc = s.has_split ? s.C - s.kc : s.C;
+  int n = 0;
+  dims5[n++] = batch;
+  dims5[n++] = zc;
+  if (p->d.ndims == 3) dims5[n++] = s.g.D;
+  dims5[n++] = s.g.H;
+  dims5[n++] = s.g.W;
+  return n;
+}
+
+static void check_call(inb_plan* p, int batch, bool want_cond) {
+  INB_CHECK(p != nullptr, "null plan");
+  INB_CHECK(p->cond == want_cond, want_cond ? "plan is not conditional (n_cond == 0)"
+                                            : "plan is conditional: use the inb_cglow_* entry points");
+  INB_CHECK(batch >= 1 && batch <= p->d.batch, "batch %d outside the plan's range [1, %d]", batch, p->d.batch);
+}
+static Ctx call_ctx(inb_plan* p, void* stream) {
+  if (!p->ar.base) {
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, p->need);
+    if (e != cudaSuccess) fail(INB_ERR_NOMEM, "workspace of %zu bytes: %s", p->need, cudaGetErrorString(e));
+    p->ar.base = (char*)base;
+    p->ar.cap = p->need;
+    p->ar.dry = false;
+    p->ar.off = 0;
+    p->ld = (double*)p->ar.alloc_bytes(256);
+    p->persist = p->ar.off;
+  }
+  p->ar.off = p->persist;
+  return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
+}
+
+int inb_glow_forward(inb_plan* p, int batch, const float* X, float* const* params, float* Z, float* logdet,
+                     int init_actnorm, void* stream) {
+  return guarded([&] {
+    check_call(p, batch, false);
+    INB_CHECK(X && params && Z, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_forward(p, c, batch, X, nullptr, params, Z, nullptr, logdet, init_actnorm);
+  });
+}
+int inb_glow_inverse(inb_plan* p, int batch, const float* Z, float* const* params, float* X, void* stream) {
+  return guarded([&] {
+    check_call(p, batch, false);
+    INB_CHECK(X && params && Z, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_reverse(p, c, batch, false, nullptr, Z, nullptr, params, nullptr, nullptr, X, nullptr);
+  });
+}
+int inb_glow_backward(inb_plan* p, int batch, const float* dZ, const float* Z, float* const* params,
+                      float* const* grads, float* dX, float* X, void* stream) {
+  return guarded([&] {
+    check_call(p, batch, false);
+    INB_CHECK(dZ && Z && params && grads && dX && X, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_reverse(p, c, batch, true, dZ, Z, nullptr, params, grads, dX, X, nullptr);
+  });
+}
+int inb_cglow_forward(inb_plan* p, int batch, const float* X, const float* C, float* const* params,
+                      float* ZX, float* ZC, float* logdet, int init_actnorm, void* stream) {
+  return guarded([&] {
+    check_call(p, batch, true);
+    INB_CHECK(X && C && params && ZX && ZC, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_forward(p, c, batch, X, C, params, ZX, ZC, logdet, init_actnorm);
+  });
+}
+int inb_cglow_inverse(inb_plan* p, int batch, const float* ZX, const float* ZC, float* const* params,
+                      float* X, void* stream) {
+  return guarded([&] {
+    check_call(p, batch, true);
+    INB_CHECK(ZX && ZC && params && X, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_reverse(p, c, batch, false, nullptr, ZX, ZC, params, nullptr, nullptr, X, nullptr);
+  });
+}
+int inb_cglow_backward(inb_plan* p, int batch, const float* dZX, const float* ZX, const float* ZC,
+                       float* const* params, float* const* grads, float* dX, float* X, float* dC,
+                       void* stream) {
+  return guarded([&] {
+    check_call(p, batch, true);
+    INB_CHECK(dZX && ZX && ZC && params && grads && dX && X && dC, "null tensor argument");
+    Ctx c = call_ctx(p, stream);
+    drive_reverse(p, c, batch, true, dZX, ZX, ZC, params, grads, dX, X, dC);
+  });
+}
+
+// ====================================================================== layer level
+int inb_actnorm_init(int B, int C, long long sp, const float* X, float* s, float* b, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && s && b && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      op_actnorm_init(c, sp, B, C, view(const_cast<float*>(X), C * sp), s, b);
+    });
+  });
+}
+int inb_actnorm_forward(int B, int C, long long sp, const float* X, const float* s, const float* b, float* Y,
+                        float* logdet, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && s && b && Y && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      double* ld = logdet ? c.ar->f64(1) : nullptr;
+      if (ld) op_zero(c, ld, sizeof(double));
+      op_an_hh_fwd(c, sp, B, C, view(const_cast<float*>(X), C * sp), view(Y, C * sp), s, b, nullptr, nullptr,
+                   nullptr, ld);
+      if (ld) op_ld_finish(c, ld, logdet);
+    });
+  });
+}
+int inb_actnorm_inverse(int B, int C, long long sp, const float* Y, const float* s, const float* b, float* X,
+                        void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && s && b && Y && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      op_hh_an_inv(c, sp, B, C, view(const_cast<float*>(Y), C * sp), view(X, C * sp), s, b, nullptr, nullptr, nullptr);
+    });
+  });
+}
+int inb_actnorm_backward(int B, int C, long long sp, const float* dY, const float* Y, const float* s,
+                         const float* b, int logdet, float* dX, float* X, float* ds, float* db, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY && Y && s && b && dX && X && ds && db && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      double* dsdb = c.ar->f64(2 * (size_t)C);
+      op_zero(c, dsdb, 2 * C * sizeof(double));
+      op_hh_an_bwd(c, sp, B, C, view(const_cast<float*>(dY), C * sp), view(const_cast<float*>(Y), C * sp),
+                   view(dX, C * sp), view(X, C * sp), s, b, nullptr, nullptr, nullptr, nullptr, dsdb);
+      op_an_grad_finish(c, C, sp, dsdb, s, logdet, ds, db);
+    });
+  });
+}
+
+int inb_conv1x1_forward(int B, int C, long long sp, const float* X, const float* v1, const float* v2,
+                        const float* v3, float* Y, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && v1 && v2 && v3 && Y && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      op_an_hh_fwd(c, sp, B, C, view(const_cast<float*>(X), C * sp), view(Y, C * sp), nullptr, nullptr, v1, v2, v3, nullptr);
+    });
+  });
+}
+int inb_conv1x1_inverse(int B, int C, long long sp, const float* Y, const float* v1, const float* v2,
+                        const float* v3, float* X, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && v1 && v2 && v3 && Y && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      op_hh_an_inv(c, sp, B, C, view(const_cast<float*>(Y), C * sp), view(X, C * sp), nullptr, nullptr, v1, v2, v3);
+    });
+  });
+}
+int inb_conv1x1_backward(int B, int C, long long sp, const float* dY, const float* Y, const float* v1,
+                         const float* v2, const float* v3, int freeze, float* dX, float* X, float* dv1,
+                         float* dv2, float* dv3, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY && Y && v1 && v2 && v3 && dX && X && dv1 && dv2 && dv3 && B > 0 && C > 0 && sp > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      double* gram = c.ar->f64((size_t)C * C);
+      op_zero(c, gram, (size_t)C * C * sizeof(double));
+      op_hh_an_bwd(c, sp, B, C, view(const_cast<float*>(dY), C * sp), view(const_cast<float*>(Y), C * sp),
+                   view(dX, C * sp), view(X, C * sp), nullptr, nullptr, v1, v2, v3, gram, nullptr);
+      op_hh_grad_finish(c, C, gram, v1, v2, v3, freeze, dv1, dv2, dv3);
+    });
+  });
+}
+
+static RBShape rb_shape_of(int ndims, int nx, int ny, int nz, int B, int Cin, int nh, int Cout, int k1, int k2) {
+  INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+  INB_CHECK(B > 0 && Cin > 0 && nh > 0 && Cout > 0, "bad shape");
+  INB_CHECK((k1 == 1 || k1 == 3) && (k2 == 1 || k2 == 3), "supported kernel sizes are 1 and 3");
+  return RBShape{make_geo(ndims, nx, ny, nz), B, Cin, 0, nh, Cout, k1, k2};
+}
+
+int inb_resblock_forward(int ndims, int nx, int ny, int nz, int B, int Cin, int nh, int Cout, int k1, int k2,
+                         int precision, const float* X, const float* W1, const float* W2, const float* W3,
+                         const float* b1, const float* b2, float* Y, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && W1 && W2 && W3 && b1 && b2 && Y, "null argument");
+    RBShape s = rb_shape_of(ndims, nx, ny, nz, B, Cin, nh, Cout, k1, k2);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      RBHidden h{c.ar->f32(rb_hidden_elems(s)), c.ar->f32(rb_hidden_elems(s)), nullptr};
+      float* Y3 = c.ar->f32((size_t)B * Cout * s.g.px);
+      rb_forward(c, s, view(const_cast<float*>(X), Cin * s.g.px), view(nullptr, 0),
+                 RBParams{W1, W2, W3, b1, b2}, h, Y3);
+      op_relu_copy(c, (long long)B * Cout * s.g.px, Y3, Y);  // layer_residual_block.jl:133
+    });
+  });
+}
+int inb_resblock_backward(int ndims, int nx, int ny, int nz, int B, int Cin, int nh, int Cout, int k1, int k2,
+                          int precision, const float* dY, const float* X, const float* W1, const float* W2,
+                          const float* W3, const float* b1, const float* b2, float* dX, float* dW1,
+                          float* dW2, float* dW3, float* db1, float* db2, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY && X && W1 && W2 && W3 && b1 && b2 && dX && dW1 && dW2 && dW3 && db1 && db2, "null argument");
+    RBShape s = rb_shape_of(ndims, nx, ny, nz, B, Cin, nh, Cout, k1, k2);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      RBHidden h{c.ar->f32(rb_hidden_elems(s)), c.ar->f32(rb_hidden_elems(s)), c.ar->f32(rb_hidden_elems(s))};
+      float* Y3 = c.ar->f32((size_t)B * Cout * s.g.px);
+      View x = view(const_cast<float*>(X), Cin * s.g.px);
+      RBParams p{W1, W2, W3, b1, b2};
+      rb_forward(c, s, x, view(nullptr, 0), p, h, Y3);                       // :143
+      op_relu_grad(c, (long long)B * Cout * s.g.px, dY, Y3, Y3);             // :150
+      rb_backward(c, s, Y3, x, view(nullptr, 0), p, h, RBGrads{dW1, dW2, dW3, db1, db2},
+                  view(dX, Cin * s.g.px), nullptr, 0, view(nullptr, 0));
+    });
+  });
+}
+
+static FlowShape coupling_shape(int ndims, int nx, int ny, int nz, int B, int C, int n_cond, int nh, int k1,
+                                int k2, float low, float high, int logdet, int freeze) {
+  INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+  INB_CHECK(B > 0 && C >= 2 && nh > 0 && n_cond >= 0, "bad shape");
+  FlowShape f{};
+  f.g = make_geo(ndims, nx, ny, nz);
+  f.B = B; f.C = C; f.ccond = n_cond; f.nh = nh; f.k1 = k1; f.k2 = k2;
+  f.low = low; f.high = high; f.logdet = logdet; f.freeze = freeze;
+  return f;
+}
+static FlowParams coupling_params(float* const* cp) {
+  FlowParams p{};
+  p.v1 = cp[0]; p.v2 = cp[1]; p.v3 = cp[2];
+  p.rb = RBParams{cp[3], cp[4], cp[5], cp[6], cp[7]};
+  return p;
+}
+
+int inb_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C, int n_cond, int nh, int k1, int k2,
+                         float low, float high, int precision, const float* X, const float* Cond,
+                         float* const* cparams, float* Y, float* logdet, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && cparams && (n_cond == 0 || Cond), "null argument");
+    FlowShape f = coupling_shape(ndims, nx, ny, nz, B, C, n_cond, nh, k1, k2, low, high, logdet != nullptr, 0);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      double* ld = logdet ? c.ar->f64(1) : nullptr;
+      if (ld) op_zero(c, ld, sizeof(double));
+      flow_forward(c, f, view(const_cast<float*>(X), C * f.g.px), view(Y, C * f.g.px),
+                   view(const_cast<float*>(Cond), n_cond * f.g.px), coupling_params(cparams), ld);
+      if (ld) op_ld_finish(c, ld, logdet);
+    });
+  });
+}
+int inb_coupling_inverse(int ndims, int nx, int ny, int nz, int B, int C, int n_cond, int nh, int k1, int k2,
+                         float low, float high, int precision, const float* Y, const float* Cond,
+                         float* const* cparams, float* X, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && cparams && (n_cond == 0 || Cond), "null argument");
+    FlowShape f = coupling_shape(ndims, nx, ny, nz, B, C, n_cond, nh, k1, k2, low, high, 0, 0);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      float* tmp = c.ar->f32((size_t)B * C * f.g.px);
+      View t = view(tmp, C * f.g.px);
+      op_copy(c, f.g.px, B, C, view(const_cast<float*>(Y), C * f.g.px), t);
+      flow_inverse(c, f, t, view(X, C * f.g.px), view(const_cast<float*>(Cond), n_cond * f.g.px),
+                   coupling_params(cparams));
+    });
+  });
+}
+int inb_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C, int n_cond, int nh, int k1, int k2,
+                          float low, float high, int logdet, int freeze, int precision, const float* dY,
+                          const float* Y, const float* Cond, float* const* cparams, float* const* cgrads,
+                          float* dX, float* X, float* dCond, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY && Y && dX && X && cparams && cgrads && (n_cond == 0 || (Cond && dCond)), "null argument");
+    FlowShape f = coupling_shape(ndims, nx, ny, nz, B, C, n_cond, nh, k1, k2, low, high, logdet, freeze);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      const long long bs = C * f.g.px;
+      View x = view(X, bs), dx = view(dX, bs);
+      op_copy(c, f.g.px, B, C, view(const_cast<float*>(Y), bs), x);
+      op_copy(c, f.g.px, B, C, view(const_cast<float*>(dY), bs), dx);
+      View dcond = view(dCond, n_cond * f.g.px);
+      if (n_cond) op_zero(c, dCond, (size_t)B * n_cond * f.g.px * sizeof(float));
+      FlowGrads g{};
+      g.v1 = cgrads[0]; g.v2 = cgrads[1]; g.v3 = cgrads[2];
+      g.rb = RBGrads{cgrads[3], cgrads[4], cgrads[5], cgrads[6], cgrads[7]};
+      flow_backward(c, f, dx, x, dx, x, view(const_cast<float*>(Cond), n_cond * f.g.px), dcond,
+                    coupling_params(cparams), g);
+    });
+  });
+}
+
+int inb_squeeze(int ndims, int nx, int ny, int nz, int B, int C, const float* X, float* Y, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && B > 0 && C > 0, "bad argument");
+    INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+    Geo g = make_geo(ndims, nx, ny, nz);
+    Arena a;
+    a.dry = false;
+    Ctx c{(cudaStream_t)stream, &a, 0};
+    op_squeeze(c, g, B, C, view(const_cast<float*>(X), C * g.px), view(Y, C * g.px));
+  });
+}
+int inb_unsqueeze(int ndims, int nx, int ny, int nz, int B, int C, const float* Y, float* X, void* stream) {
+  return guarded([&] {
+    // (nx,ny,nz) and C describe the squeezed tensor Y (dimensionality_operations.jl:137-166)
+    INB_CHECK(X && Y && B > 0 && C > 0, "bad argument");
+    INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+    INB_CHECK(C % (1 << ndims) == 0, "number of channels must be divisible by %d", 1 << ndims);  // :141-143
+    Geo gs = make_geo(ndims, nx, ny, nz);
+    Geo g = make_geo(ndims, nx * 2, ny * 2, nz * 2);
+    Arena a;
+    Ctx c{(cudaStream_t)stream, &a, 0};
+    op_unsqueeze(c, g, B, C >> ndims, view(const_cast<float*>(Y), C * gs.px), view(X, C * gs.px));
+  });
+}
+
+int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, void* stream) {
+  return guarded([&] {
+    INB_CHECK(Z && n > 0 && B > 0, "bad argument");
+    with_temp_arena((cudaStream_t)stream, 0, [&](Ctx& c) {
+      double* acc = loss ? c.ar->f64(1) : nullptr;
+      op_nll_grad(c, n, B, Z, dZ, acc, loss);
+    });
+  });
+}
+
+}  // extern "C"

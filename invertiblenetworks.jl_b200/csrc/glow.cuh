@@ -1,0 +1,68 @@
+// glow.cuh - layer compositions shared by the layer-level and network-level entry points.
+#pragma once
+#include "ops.cuh"
+
+namespace inb {
+
+struct RBShape {
+  Geo g;
+  int B;
+  int c0;    // channels taken from the flow tensor (X2)
+  int ccond; // channels taken from the condition (0 when unconditional)
+  int nh;
+  int Cout;
+  int k1, k2;
+  int Cin() const { return c0 + ccond; }
+  int T1() const { return k1 == 1 ? 1 : (g.nd == 3 ? 27 : 9); }
+  int T2() const { return k2 == 1 ? 1 : (g.nd == 3 ? 27 : 9); }
+};
+struct RBParams {
+  const float *W1, *W2, *W3, *b1, *b2;
+};
+struct RBGrads {
+  float *W1, *W2, *W3, *b1, *b2;
+};
+// hidden activations of one block, owned by the caller's arena
+struct RBHidden {
+  float* Y1;  // (B, nh, px) pre-activation of conv1
+  float* Y2;  // (B, nh, px) pre-activation of conv2 (+skip)
+  float* G;   // (B, nh, px) gradient scratch (backward only)
+};
+
+// layer_residual_block.jl:119-134, output = PRE-activation Y3 (B, Cout, px) compact; the consumers
+// apply the final ReLU (:133) themselves.
+void rb_forward(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3);
+// layer_residual_block.jl:137-178 given the already ReLU-masked dY3 (:150) and the hidden
+// activations of rb_forward.  dX2 (+= passthrough `add` when non-null) and dCond (accumulated).
+void rb_backward(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
+                 RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs,
+                 View dcond);
+
+struct FlowShape {
+  Geo g;
+  int B, C, ccond, nh, k1, k2;
+  float low, high;
+  int logdet, freeze;
+  int C1() const { return split_k(C); }
+  RBShape rb() const { return RBShape{g, B, C - C1(), ccond, nh, 2 * C1(), k1, k2}; }
+};
+struct FlowParams {
+  const float *s, *b;  // ActNorm (nullable: coupling layer alone)
+  const float *v1, *v2, *v3;
+  RBParams rb;
+};
+struct FlowGrads {
+  float *s, *b, *v1, *v2, *v3;
+  RBGrads rb;
+};
+size_t rb_hidden_elems(const RBShape& s);
+
+// ActNorm -> CouplingLayerGlow forward: x -> y (y != x)
+void flow_forward(Ctx& c, const FlowShape& f, View x, View y, View cond, const FlowParams& p, double* ld);
+// CouplingLayerGlow.inverse -> ActNorm.inverse: y (clobbered) -> x
+void flow_inverse(Ctx& c, const FlowShape& f, View y, View x, View cond, const FlowParams& p);
+// backward of both; (dy, y) are clobbered and (dx, x) may alias them
+void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x, View cond, View dcond,
+                   const FlowParams& p, const FlowGrads& g);
+
+}  // namespace inb

@@ -1,0 +1,213 @@
+// layers.cu - ResidualBlock and flow-step (ActNorm -> Conv1x1 -> affine coupling) compositions.
+#include "glow.cuh"
+#include <algorithm>
+
+namespace inb {
+
+size_t rb_hidden_elems(const RBShape& s) { return (size_t)s.B * s.nh * s.g.px; }
+
+static ConvSpec conv_base(const RBShape& s) {
+  ConvSpec cs{};
+  cs.g = s.g;
+  cs.B = s.B;
+  cs.add_n = 1 << 30;
+  return cs;
+}
+
+// ---------------------------------------------------------------- ResidualBlock, fp32 SIMT
+static void rb_forward_fp32(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h,
+                            float* Y3) {
+  const long long px = s.g.px;
+  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2();
+  size_t m = c.ar->mark();
+  float* Wm1 = c.ar->f32((size_t)T1 * Cin * nh);
+  float* Wm2 = c.ar->f32((size_t)T2 * nh * nh);
+  float* Wm3 = c.ar->f32((size_t)T1 * nh * s.Cout);
+  op_pack_w(c, PACK_CONV, nh, Cin, T1, p.W1, Wm1);
+  op_pack_w(c, PACK_CONV, nh, nh, T2, p.W2, Wm2);
+  op_pack_w(c, PACK_DATA, nh, s.Cout, T1, p.W3, Wm3);
+  {  // Y1 = conv(X, W1) + b1                                  layer_residual_block.jl:122
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k1;
+    cs.in0 = x2.p; cs.in0_bs = x2.bs; cs.c0 = s.c0;
+    cs.in1 = cond.p; cs.in1_bs = cond.bs;
+    cs.Cin = Cin; cs.Wm = Wm1; cs.N = nh;
+    cs.out0 = h.Y1; cs.out0_bs = (long long)nh * px; cs.n0 = nh;
+    cs.bias = p.b1;
+    op_conv_simt(c, cs);
+  }
+  {  // Y2 = X2 + conv(X2, W2) + b2, X2 = relu(Y1)             :123-125
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k2;
+    cs.in0 = h.Y1; cs.in0_bs = (long long)nh * px; cs.c0 = nh; cs.Cin = nh; cs.relu_in = 1;
+    cs.Wm = Wm2; cs.N = nh;
+    cs.out0 = h.Y2; cs.out0_bs = (long long)nh * px; cs.n0 = nh;
+    cs.bias = p.b2;
+    cs.add = h.Y1; cs.add_bs = (long long)nh * px; cs.add_relu = 1;
+    op_conv_simt(c, cs);
+  }
+  {  // Y3 = \nabla conv_data(X3, W3), X3 = relu(Y2)            :126-129
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k1;
+    cs.in0 = h.Y2; cs.in0_bs = (long long)nh * px; cs.c0 = nh; cs.Cin = nh; cs.relu_in = 1;
+    cs.Wm = Wm3; cs.N = s.Cout;
+    cs.out0 = Y3; cs.out0_bs = (long long)s.Cout * px; cs.n0 = s.Cout;
+    op_conv_simt(c, cs);
+  }
+  c.ar->release(m);
+}
+
+static void rb_backward_fp32(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond,
+                             const RBParams& p, RBHidden& h, const RBGrads& gr, View dx2,
+                             const float* add, long long add_bs, View dcond) {
+  const long long px = s.g.px;
+  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2(), Cout = s.Cout;
+  const long long hbs = (long long)nh * px;
+  size_t m = c.ar->mark();
+  size_t wmax = std::max((size_t)T1 * std::max(Cin, Cout) * nh, (size_t)T2 * nh * nh);
+  float* Wm = c.ar->f32(wmax);
+  float* dWm = c.ar->f32(wmax);
+  float* G2 = h.G;   // dY2
+  float* G1 = h.Y2;  // dY1 reuses the Y2 buffer once dW3 has consumed relu(Y2)
+
+  // dX3 = conv(dY3, W3); dY2 = relugrad(dX3, Y2)               layer_residual_block.jl:151,154
+  op_pack_w(c, PACK_CONV, nh, Cout, T1, p.W3, Wm);
+  {
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k1;
+    cs.in0 = dY3; cs.in0_bs = (long long)Cout * px; cs.c0 = Cout; cs.Cin = Cout;
+    cs.Wm = Wm; cs.N = nh;
+    cs.out0 = G2; cs.out0_bs = hbs; cs.n0 = nh;
+    cs.mask = h.Y2; cs.mask_bs = hbs;
+    op_conv_simt(c, cs);
+  }
+  {  // dW3 = \nabla conv_filter(dY3, X3)                         :152
+    WgradSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k1;
+    ws.in0 = dY3; ws.in0_bs = (long long)Cout * px; ws.c0 = Cout; ws.Cin = Cout;
+    ws.dy = h.Y2; ws.dy_bs = hbs; ws.N = nh; ws.relu_dy = 1;
+    ws.dWm = dWm;
+    op_wgrad_simt(c, ws);
+    op_unpack_dw(c, nh, Cout, T1, dWm, gr.W3);
+  }
+  // dX2 = \nabla conv_data(dY2, W2) + dY2; dY1 = relugrad(dX2, Y1)   :155,161
+  op_pack_w(c, PACK_DATA, nh, nh, T2, p.W2, Wm);
+  {
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k2;
+    cs.in0 = G2; cs.in0_bs = hbs; cs.c0 = nh; cs.Cin = nh;
+    cs.Wm = Wm; cs.N = nh;
+    cs.out0 = G1; cs.out0_bs = hbs; cs.n0 = nh;
+    cs.add = G2; cs.add_bs = hbs;
+    cs.mask = h.Y1; cs.mask_bs = hbs;
+    op_conv_simt(c, cs);
+  }
+  {  // dW2 = \nabla conv_filter(X2, dY2); db2 = sum dY2          :156-157
+    WgradSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k2;
+    ws.in0 = h.Y1; ws.in0_bs = hbs; ws.c0 = nh; ws.Cin = nh; ws.relu_in = 1;
+    ws.dy = G2; ws.dy_bs = hbs; ws.N = nh;
+    ws.dWm = dWm;
+    op_wgrad_simt(c, ws);
+    op_unpack_dw(c, nh, nh, T2, dWm, gr.W2);
+    op_channel_sum(c, px, s.B, nh, G2, gr.b2);
+  }
+  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)              :162
+  op_pack_w(c, PACK_DATA, nh, Cin, T1, p.W1, Wm);
+  {
+    ConvSpec cs = conv_base(s);
+    cs.k = s.k1;
+    cs.in0 = G1; cs.in0_bs = hbs; cs.c0 = nh; cs.Cin = nh;
+    cs.Wm = Wm; cs.N = Cin;
+    cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;
+    cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
+    cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
+    op_conv_simt(c, cs);
+  }
+  {  // dW1 = \nabla conv_filter(X1, dY1); db1 = sum dY1          :163-164
+    WgradSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k1;
+    ws.in0 = x2.p; ws.in0_bs = x2.bs; ws.c0 = s.c0; ws.in1 = cond.p; ws.in1_bs = cond.bs; ws.Cin = Cin;
+    ws.dy = G1; ws.dy_bs = hbs; ws.N = nh;
+    ws.dWm = dWm;
+    op_wgrad_simt(c, ws);
+    op_unpack_dw(c, nh, Cin, T1, dWm, gr.W1);
+    op_channel_sum(c, px, s.B, nh, G1, gr.b1);
+  }
+  c.ar->release(m);
+}
+
+void rb_forward(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
+  INB_CHECK(c.prec == 0, "precision mode %d is not available in this build", c.prec);
+  rb_forward_fp32(c, s, x2, cond, p, h, Y3);
+}
+void rb_backward(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
+                 RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs, View dcond) {
+  INB_CHECK(c.prec == 0, "precision mode %d is not available in this build", c.prec);
+  rb_backward_fp32(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
+}
+
+// ---------------------------------------------------------------- flow step
+void flow_forward(Ctx& c, const FlowShape& f, View x, View y, View cond, const FlowParams& p, double* ld) {
+  const long long px = f.g.px;
+  const int C1 = f.C1();
+  const RBShape rs = f.rb();
+  size_t m = c.ar->mark();
+  // Y = ActNorm(X) (actnorm.jl:73), X_ = C.forward(Y) (glow.jl:105)
+  op_an_hh_fwd(c, px, f.B, f.C, x, y, p.s, p.b, p.v1, p.v2, p.v3, f.logdet ? ld : nullptr);
+  RBHidden h;
+  h.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  h.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  h.G = nullptr;
+  float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
+  rb_forward(c, rs, sub(y, C1, px), cond, p.rb, h, Y3);  // glow.jl:109, X2 = second part
+  op_coupling_fwd(c, px, f.B, C1, y, y, Y3, f.low, f.high, f.logdet ? ld : nullptr);  // :110-116
+  c.ar->release(m);
+}
+
+void flow_inverse(Ctx& c, const FlowShape& f, View y, View x, View cond, const FlowParams& p) {
+  const long long px = f.g.px;
+  const int C1 = f.C1();
+  const RBShape rs = f.rb();
+  size_t m = c.ar->mark();
+  RBHidden h;
+  h.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  h.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  h.G = nullptr;
+  float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
+  rb_forward(c, rs, sub(y, C1, px), cond, p.rb, h, Y3);             // glow.jl:124
+  op_coupling_inv(c, px, f.B, C1, y, y, Y3, f.low, f.high);        // :127
+  op_hh_an_inv(c, px, f.B, f.C, y, x, p.s, p.b, p.v1, p.v2, p.v3); // :130, actnorm.jl:93
+  c.ar->release(m);
+}
+
+void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x, View cond, View dcond,
+                   const FlowParams& p, const FlowGrads& g) {
+  const long long px = f.g.px;
+  const int C1 = f.C1(), C = f.C;
+  const RBShape rs = f.rb();
+  size_t m = c.ar->mark();
+  RBHidden h;
+  h.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  h.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  h.G = c.ar->f32(rb_hidden_elems(rs));
+  float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
+  double* gram = c.ar->f64((size_t)C * C + 2 * C);
+  double* dsdb = gram + (size_t)C * C;
+  op_zero(c, gram, ((size_t)C * C + 2 * C) * sizeof(double));
+  View y2 = sub(y, C1, px), dy2 = sub(dy, C1, px);
+  // recompute the block once (glow.jl:139 -> :124; the reference recomputes it again at
+  // layer_residual_block.jl:143 - same values)
+  rb_forward(c, rs, y2, cond, p.rb, h, Y3);
+  // X1, dX1, and the masked gradient of the block output        glow.jl:127,142-151
+  op_coupling_bwd(c, px, f.B, C1, y, y, dy, dy, Y3, f.low, f.high, f.logdet);
+  // dX2 = RB.backward(...) + dY2                                 glow.jl:151
+  rb_backward(c, rs, Y3, y2, cond, p.rb, h, g.rb, dy2, dy2.p, dy2.bs, dcond);
+  // Conv1x1 inverse on (dX_, X_) + ActNorm backward              glow.jl:159, actnorm.jl:100-123
+  op_hh_an_bwd(c, px, f.B, C, dy, y, dx, x, p.s, p.b, p.v1, p.v2, p.v3, gram, p.s ? dsdb : nullptr);
+  op_hh_grad_finish(c, C, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3);
+  if (p.s) op_an_grad_finish(c, C, px, dsdb, p.s, f.logdet, g.s, g.b);
+  c.ar->release(m);
+}
+
+}  // namespace inb
