@@ -1,0 +1,72 @@
+// conv_tc.cuh - tcgen05 tensor-core path of the ResidualBlock contractions (INB_PREC_BF16X3 / BF16).
+//
+// Internal layout: pixel-major "NHWC" bf16, row = pixel m = ((b*D+z)*H+y)*W+x, `pitch` channels per
+// row.  Every fp32 value v is held as two bf16 planes hi = RN(v), lo = RN(v - hi); BF16X3 evaluates
+// a*b as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (fp32 accumulate in TMEM), BF16 uses the hi planes only.
+// A hidden activation X = relu(Y) stores -0.0 where Y < 0 and +0.0 where Y == 0, so the sign bit of
+// the hi plane is the _relugrad mask (activation_functions.jl:84) while the MMA still sees zero.
+#pragma once
+#include "ops.cuh"
+#include <cuda_bf16.h>
+
+namespace inb {
+
+struct Planes {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  int pitch;  // channels per row
+};
+
+// tile geometry of a P-pixel TMA box over (W,H,D,B); ok == false when the shape cannot be tiled
+struct TileBox {
+  int wt, ht, dt, bt;
+  bool ok;
+};
+TileBox make_tile_box(const Geo& g, int B, int P);
+bool tc_geometry_ok(const Geo& g, int B);
+
+// (B,C,px) fp32 [two sources, conditional cat] -> planes [M][cpad] (channels >= Cin are zero)
+void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_bs, int c0, const float* in1,
+                   long long in1_bs, int Cin, int cpad, Planes out);
+// reference weight (C order w[d0][d1][T]) -> planes [npad][T*cpad] (K-major rows), mode PACK_CONV/PACK_DATA
+void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int cpad, Planes out);
+// per-channel sum over rows of planes [M][C] -> out[C] (bias gradients)
+void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out);
+
+struct ConvTcSpec {
+  Geo g;
+  int B;
+  int k;          // 1 or 3
+  Planes in;      // [M][cpad_in]
+  int cpad_in;    // multiple of 16
+  Planes w;       // [npad][T*cpad_in]
+  int N;          // MMA N = npad (multiple of 16, <= 256)
+  int n_real;
+  const float* bias;
+  // mode 0: planes output (hidden / gradient of hidden)
+  int mode;
+  Planes out;
+  int relu_encode;
+  Planes skip;    // added (hi+lo), nullable
+  Planes mask;    // sign bit of hi -> zero the value, nullable
+  // mode 1: fp32 (B,C,px) output
+  float* out0; long long out0_bs; int n0;
+  float* out1; long long out1_bs; int out1_accum;
+  const float* add; long long add_bs; int add_n;
+};
+void op_conv_tc(Ctx& c, const ConvTcSpec& s);
+
+struct WgradTcSpec {
+  Geo g;
+  int B;
+  int k;
+  Planes P;       // unshifted operand, [M][np] with np = number of its channels (multiple of 128)
+  int np;
+  Planes Q;       // tap-shifted operand, [M][cq]
+  int cq;         // padded channels of Q (multiple of 16)
+  int cq_real;
+  float* dw;      // += D[tap][p][q] at ((p*cq_real + q)*T + (T-1-tap)); zeroed by the op
+};
+void op_wgrad_tc(Ctx& c, const WgradTcSpec& s);
+
+}  // namespace inb

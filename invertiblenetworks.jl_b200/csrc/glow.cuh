@@ -1,6 +1,7 @@
 // glow.cuh - layer compositions shared by the layer-level and network-level entry points.
 #pragma once
 #include "ops.cuh"
+#include "conv_tc.cuh"
 
 namespace inb {
 
@@ -27,6 +28,9 @@ struct RBHidden {
   float* Y1;  // (B, nh, px) pre-activation of conv1
   float* Y2;  // (B, nh, px) pre-activation of conv2 (+skip)
   float* G;   // (B, nh, px) gradient scratch (backward only)
+  // tensor-core path: the same three buffers hold bf16 hi/lo planes [M][nh]; xin is the padded
+  // bf16 copy of the block input made by rb_forward (lives in the caller's arena scope)
+  Planes xin{nullptr, nullptr, 0};
 };
 
 // layer_residual_block.jl:119-134, output = PRE-activation Y3 (B, Cout, px) compact; the consumers

@@ -137,14 +137,142 @@ static void rb_backward_fp32(Ctx& c, const RBShape& s, const float* dY3, View x2
   c.ar->release(m);
 }
 
+// ---------------------------------------------------------------- ResidualBlock, tcgen05 path
+static int pad16(int n) { return (n + 15) / 16 * 16; }
+
+static void tc_check(const RBShape& s) {
+  INB_CHECK(s.nh % 128 == 0 && s.nh <= 256,
+            "the tensor-core path needs n_hidden in {128, 256} (got %d); use precision fp32", s.nh);
+  INB_CHECK(pad16(s.Cin()) <= 256 && pad16(s.Cout) <= 256, "the tensor-core path supports up to 256 channels");
+  INB_CHECK(tc_geometry_ok(s.g, s.B),
+            "spatial size %dx%dx%d cannot be tiled for the tensor-core path; use precision fp32", s.g.W, s.g.H, s.g.D);
+}
+static Planes planes_at(void* mem, long long M, int pitch) {
+  Planes p;
+  p.hi = reinterpret_cast<__nv_bfloat16*>(mem);
+  p.lo = p.hi + M * pitch;
+  p.pitch = pitch;
+  return p;
+}
+static Planes planes_new(Ctx& c, long long rows, int pitch) {
+  return planes_at(c.ar->alloc_bytes((size_t)rows * pitch * 2 * 2), rows, pitch);
+}
+static ConvTcSpec tc_base(const RBShape& s) {
+  ConvTcSpec cs{};
+  cs.g = s.g;
+  cs.B = s.B;
+  cs.add_n = 1 << 30;
+  return cs;
+}
+
+static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
+  tc_check(s);
+  const long long px = s.g.px, M = px * s.B;
+  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2();
+  const int cin_pad = pad16(Cin), cout_pad = pad16(s.Cout);
+  // the padded bf16 copy of the block input outlives this call (wgrad1 reads it again)
+  h.xin = planes_new(c, M, cin_pad);
+  op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
+  size_t m = c.ar->mark();
+  Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
+  Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, T2 * nh), W3 = planes_new(c, cout_pad, T1 * nh);
+  op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
+  op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2);
+  op_pack_w_tc(c, PACK_DATA, nh, s.Cout, T1, p.W3, cout_pad, nh, W3);
+  {  // X2 = relu(conv(X, W1) + b1)                           layer_residual_block.jl:122-123
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k1; cs.in = h.xin; cs.cpad_in = cin_pad; cs.w = W1; cs.N = nh; cs.n_real = nh; cs.bias = p.b1;
+    cs.mode = 0; cs.out = H1; cs.relu_encode = 1;
+    op_conv_tc(c, cs);
+  }
+  {  // X3 = relu(X2 + conv(X2, W2) + b2)                      :125-126
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k2; cs.in = H1; cs.cpad_in = nh; cs.w = W2; cs.N = nh; cs.n_real = nh; cs.bias = p.b2;
+    cs.mode = 0; cs.out = H2; cs.relu_encode = 1; cs.skip = H1;
+    op_conv_tc(c, cs);
+  }
+  {  // Y3 = \nabla conv_data(X3, W3)                           :128-129
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k1; cs.in = H2; cs.cpad_in = nh; cs.w = W3; cs.N = cout_pad; cs.n_real = s.Cout;
+    cs.mode = 1; cs.out0 = Y3; cs.out0_bs = (long long)s.Cout * px; cs.n0 = s.Cout;
+    op_conv_tc(c, cs);
+  }
+  c.ar->release(m);
+}
+
+static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
+                           RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs,
+                           View dcond) {
+  tc_check(s);
+  const long long px = s.g.px, M = px * s.B;
+  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2(), Cout = s.Cout;
+  const int cin_pad = pad16(Cin), cout_pad = pad16(Cout);
+  size_t m = c.ar->mark();
+  Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh), G2 = planes_at(h.G, M, nh);
+  Planes G1 = H2;  // dY1 reuses X3's storage once dW3 and the dgrad3 mask have consumed it
+  Planes dY3p = planes_new(c, M, cout_pad);
+  op_nchw_to_tc(c, s.g, s.B, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, cout_pad, dY3p);
+  const int kmax = std::max(T1 * std::max(cout_pad, nh), T2 * nh);
+  Planes Wp = planes_new(c, std::max(nh, cin_pad), kmax);
+  auto wview = [&](int rows, int k) { return planes_at(Wp.hi, rows, k); };
+  {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
+    Planes W = wview(nh, T1 * cout_pad);
+    op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W);
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k1; cs.in = dY3p; cs.cpad_in = cout_pad; cs.w = W; cs.N = nh; cs.n_real = nh;
+    cs.mode = 0; cs.out = G2; cs.mask = H2;
+    op_conv_tc(c, cs);
+  }
+  {  // dW3 = \nabla conv_filter(dY3, X3)                        :152
+    WgradTcSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k1; ws.P = H2; ws.np = nh; ws.Q = dY3p; ws.cq = cout_pad; ws.cq_real = Cout;
+    ws.dw = gr.W3;
+    op_wgrad_tc(c, ws);
+  }
+  {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
+    Planes W = wview(nh, T2 * nh);
+    op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W);
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k2; cs.in = G2; cs.cpad_in = nh; cs.w = W; cs.N = nh; cs.n_real = nh;
+    cs.mode = 0; cs.out = G1; cs.skip = G2; cs.mask = H1;
+    op_conv_tc(c, cs);
+  }
+  {  // dW2 = \nabla conv_filter(X2, dY2); db2 = sum dY2         :156-157
+    WgradTcSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k2; ws.P = G2; ws.np = nh; ws.Q = H1; ws.cq = nh; ws.cq_real = nh;
+    ws.dw = gr.W2;
+    op_wgrad_tc(c, ws);
+    op_colsum_tc(c, M, nh, G2, gr.b2);
+  }
+  {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
+    Planes W = wview(cin_pad, T1 * nh);
+    op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, W);
+    ConvTcSpec cs = tc_base(s);
+    cs.k = s.k1; cs.in = G1; cs.cpad_in = nh; cs.w = W; cs.N = cin_pad; cs.n_real = Cin;
+    cs.mode = 1; cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;
+    cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
+    cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
+    op_conv_tc(c, cs);
+  }
+  {  // dW1 = \nabla conv_filter(X1, dY1); db1 = sum dY1         :163-164
+    WgradTcSpec ws{};
+    ws.g = s.g; ws.B = s.B; ws.k = s.k1; ws.P = G1; ws.np = nh; ws.Q = h.xin; ws.cq = cin_pad; ws.cq_real = Cin;
+    ws.dw = gr.W1;
+    op_wgrad_tc(c, ws);
+    op_colsum_tc(c, M, nh, G1, gr.b1);
+  }
+  (void)x2; (void)cond;
+  c.ar->release(m);
+}
+
 void rb_forward(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
-  INB_CHECK(c.prec == 0, "precision mode %d is not available in this build", c.prec);
-  rb_forward_fp32(c, s, x2, cond, p, h, Y3);
+  if (c.prec == 0) rb_forward_fp32(c, s, x2, cond, p, h, Y3);
+  else rb_forward_tc(c, s, x2, cond, p, h, Y3);
 }
 void rb_backward(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
                  RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs, View dcond) {
-  INB_CHECK(c.prec == 0, "precision mode %d is not available in this build", c.prec);
-  rb_backward_fp32(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
+  if (c.prec == 0) rb_backward_fp32(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
+  else rb_backward_tc(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
 }
 
 // ---------------------------------------------------------------- flow step

@@ -46,3 +46,48 @@ def clone_oracle(make, dtype):
         if q.data is not None:
             p.data = q.data.to(dtype)
     return n
+
+
+class FragileUnits:
+    """Counts ReLU units whose pre-activation is within `thr` (relative to the tensor's rms) of zero
+    while the float64 oracle runs its backward.  At such a unit _relugrad (activation_functions.jl:84)
+    is discontinuous: ANY arithmetic that is not bit-identical (the reference's own fp32 on another
+    BLAS included) may take the other branch, and the gradient then differs by O(1) around that unit.
+    Parity of gradients is therefore asserted strictly when no unit is fragile, and through the median
+    elementwise error when the oracle itself reports fragile units (assert_grad_close)."""
+
+    def __init__(self, thr):
+        self.thr, self.count, self.total = thr, 0, 0
+
+    def __enter__(self):
+        self._orig = O.relu_grad
+
+        def counted(dy, x):
+            rms = x.pow(2).mean().sqrt()
+            self.count += int((x.abs() < self.thr * rms).sum())
+            self.total += x.numel()
+            return self._orig(dy, x)
+        O.relu_grad = counted
+        return self
+
+    def __exit__(self, *a):
+        O.relu_grad = self._orig
+
+
+def median_err(a, b):
+    """median elementwise |a - b| relative to rms(b): insensitive to the few elements a flipped unit touches"""
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    return ((a - b).abs().median() / b.pow(2).mean().sqrt()).item()
+
+
+def assert_grad_close(a, b, tol, fragile, what=""):
+    """strict relative-L2 parity; when the float64 oracle itself reports fragile ReLU units the strict
+    bound may be missed around those units only: then the median elementwise error must still meet
+    `tol` (a systematic error would move every element) and the L2 error stays below 5e-2."""
+    r = rel(a, b)
+    if r < tol:
+        return
+    assert fragile is not None and fragile.count > 0, f"{what}: {r} >= {tol} and no fragile ReLU unit explains it"
+    med = median_err(a, b)
+    assert med < tol and r < 5e-2, f"{what}: rel {r}, median {med} (fragile ReLU units: {fragile.count}/{fragile.total})"

@@ -5,7 +5,7 @@ and size-independent properties at larger sizes."""
 import pytest
 import torch
 
-from _util import O, TOL_GRAD, TOL_LOGDET, TOL_OUT, clone_oracle, rel
+from _util import O, TOL_GRAD, TOL_LOGDET, TOL_OUT, FragileUnits, assert_grad_close, clone_oracle, rel
 
 import inb200
 
@@ -18,7 +18,7 @@ def g(t):
 
 
 def run_glow_parity(n_in, nh, L, K, shape, *, logdet=True, split=True, ndims=2, tol_out=TOL_OUT,
-                    tol_grad=TOL_GRAD, precision="fp32", seed=11):
+                    tol_grad=TOL_GRAD, precision="fp32", seed=11, fragile_thr=1e-6, inv_tol=1e-5):
     torch.manual_seed(seed)
     mk = lambda dt: O.NetworkGlow(n_in, nh, L, K, logdet=logdet, split_scales=split, ndims=ndims, seed=3, dtype=dt,
                                   faithful=False)
@@ -44,20 +44,21 @@ def run_glow_parity(n_in, nh, L, K, shape, *, logdet=True, split=True, ndims=2, 
     # invertibility, reference bound 1f-5 (test_glow.jl:46)
     Xi = G.inverse(Z)
     inv_cuda, inv_oracle = rel(Xi, X), rel(G32.inverse(Z32), X)
-    assert inv_cuda < max(1e-5, 2 * inv_oracle)
+    assert inv_cuda < max(inv_tol, 2 * inv_oracle)
     # backward from the same (float64-rounded-to-float32) latent
     Zin = Z64.float()
     dZ = Zin / shape[0]
     dX, Xr = G.backward(g(dZ), g(Zin))
-    dX64, X64 = G64.backward(dZ.double(), Zin.double())
-    assert rel(Xr, X64) < tol_out and rel(dX, dX64) < tol_out
+    with FragileUnits(fragile_thr) as fr:
+        dX64, X64 = G64.backward(dZ.double(), Zin.double())
+    assert rel(Xr, X64) < tol_out
+    assert_grad_close(dX, dX64, tol_out, fr, "dX")
     ps, qs = G.get_params(), G64.get_params()
     assert sum(p.grad is not None for p in ps) == 10 * L * K  # test_glow.jl:50-62
     worst = 0.0
     for i, (p, q) in enumerate(zip(ps, qs)):
-        e = rel(p.grad, q.grad)
-        worst = max(worst, e)
-        assert e < tol_grad, f"gradient {i}: {e}"
+        worst = max(worst, rel(p.grad, q.grad))
+        assert_grad_close(p.grad, q.grad, tol_grad, fr, f"gradient {i}")
     inb200.clear_grad(G)
     assert all(p.grad is None for p in G.get_params())  # test_glow.jl:64-66
     return worst

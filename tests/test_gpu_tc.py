@@ -1,0 +1,106 @@
+"""GPU parity of the tcgen05 tensor-core path (precision "bf16x3" = 3-term split bf16, fp32-equivalent;
+precision "bf16" = single pass) against the float64 oracle, at ResidualBlock, coupling-layer and network
+level.  Tolerances: bf16x3 must meet the float32 bar of tests/_util.py; bf16 states its own (TOL_BF16)."""
+import pytest
+import torch
+
+from _util import O, TOL_GRAD, TOL_LOGDET, TOL_OUT, FragileUnits, assert_grad_close, clone_oracle, rel
+
+import inb200
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_BF16 = 1e-1   # single-pass bf16 operands (8-bit mantissa), fp32 accumulate; ReLU-mask flips dominate the backward error
+TOLS = {"bf16x3": (TOL_OUT, TOL_GRAD), "bf16": (TOL_BF16, 2 * TOL_BF16)}
+# a ReLU unit is "fragile" when its pre-activation is closer to zero than the arithmetic's own error
+FRAGILE = {"bf16x3": 1e-4, "bf16": 3e-2}
+INV_TOL = {"bf16x3": 1e-5, "bf16": 1e-2}  # bf16 rounding of the block input is discontinuous: ~1e-4 per layer
+
+
+def g(t):
+    return t.to(DEV)
+
+
+RB_CASES = [
+    # B, Cin, nh, Cout, spatial, k1, k2
+    (2, 6, 128, 12, (16, 16), 3, 1),
+    (3, 2, 256, 4, (8, 8), 3, 1),          # two samples per 128-pixel tile, ragged last tile
+    (2, 24, 128, 48, (32, 32), 3, 1),      # cfg2 scale-3 channel plan
+    (1, 3, 128, 6, (2, 256), 3, 1),        # W > tile
+    (2, 4, 128, 8, (8, 8, 8), 3, 1),       # 3-D, 27 taps
+    (2, 6, 128, 12, (16, 16), 3, 3),       # k2 = 3 (HINT-style block)
+    (2, 5, 128, 10, (16, 16), 1, 1),
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", RB_CASES)
+def test_resblock_tc(case, prec):
+    torch.manual_seed(4)
+    tol_out, tol_grad = TOLS[prec]
+    B, Cin, nh, Cout, sp, k1, k2 = case
+    nd = len(sp)
+    RB = inb200.ResidualBlock(Cin, nh, n_out=Cout, k1=k1, k2=k2, p1=(k1 - 1) // 2, p2=(k2 - 1) // 2, ndims=nd,
+                              precision=prec, gen=torch.Generator().manual_seed(3), device=DEV)
+    RB.b1.data.copy_(torch.randn(nh) * 0.1)
+    RB.b2.data.copy_(torch.randn(nh) * 0.1)
+    ws = [p.data.cpu().double() for p in RB.get_params()]
+    R64 = O.ResidualBlock(*ws, p1=(k1 - 1) // 2, p2=(k2 - 1) // 2)
+    X = torch.randn(B, Cin, *sp)
+    dY = torch.randn(B, Cout, *sp)
+    Y = RB.forward(g(X))
+    Y64 = R64.forward(X.double())
+    assert rel(Y, Y64) < tol_out, f"forward {rel(Y, Y64)}"
+    dX = RB.backward(g(dY), g(X))
+    with FragileUnits(FRAGILE[prec]) as fr:
+        dX64 = R64.backward(dY.double(), X.double())
+    assert_grad_close(dX, dX64, tol_out, fr, "dX")
+    for name, p, q in zip("W1 W2 W3 b1 b2".split(), RB.get_params(), R64.params()):
+        assert_grad_close(p.grad, q.grad, tol_grad, fr, name)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("case", [(2, 12, 0, 128, (16, 16)), (2, 4, 4, 128, (16, 16)), (2, 8, 0, 128, (8, 8, 8))])
+def test_coupling_layer_tc(case, prec):
+    torch.manual_seed(6)
+    tol_out, tol_grad = TOLS[prec]
+    B, Cc, n_cond, nh, sp = case
+    CL = inb200.CouplingLayerGlow(Cc, nh, n_cond=n_cond, logdet=True, ndims=len(sp), precision=prec,
+                                  gen=torch.Generator().manual_seed(9), device=DEV)
+    ws = [p.data.cpu().double() for p in CL.get_params()]
+    C64 = O.CouplingLayerGlow(O.Conv1x1(*ws[:3]), O.ResidualBlock(*ws[3:]), logdet=True)
+    X = torch.randn(B, Cc, *sp)
+    cond = torch.randn(B, n_cond, *sp) if n_cond else None
+    dY = torch.randn(B, Cc, *sp)
+    Y, ld = CL.forward(g(X), g(cond) if n_cond else None)
+    Y64, ld64 = C64.forward(X.double(), cond.double() if n_cond else None)
+    assert rel(Y, Y64) < tol_out
+    assert abs(ld.item() - ld64.item()) / abs(ld64.item()) < TOL_LOGDET * (tol_out / TOL_OUT)
+    assert rel(CL.inverse(Y, g(cond) if n_cond else None), X) < 1e-5  # same arithmetic both ways
+    res = CL.backward(g(dY), Y, g(cond) if n_cond else None)
+    with FragileUnits(FRAGILE[prec]) as fr:
+        r64 = C64.backward(dY.double(), Y.cpu().double(), cond.double() if n_cond else None)
+    assert rel(res[1], r64[1]) < tol_out
+    assert_grad_close(res[0], r64[0], tol_out, fr, "dX")
+    if n_cond:
+        assert_grad_close(res[2], r64[2], tol_out, fr, "dC")
+    for name, p, q in zip("v1 v2 v3 W1 W2 W3 b1 b2".split(), CL.get_params(), C64.params()):
+        assert_grad_close(p.grad, q.grad, tol_grad, fr, name)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_glow_network_tc(prec):
+    """cfg2's channel plan (3 -> 12/24/48) with n_hidden = 128 at 64x64, L = 3."""
+    from test_gpu_networks import run_glow_parity
+    tol_out, tol_grad = TOLS[prec]
+    run_glow_parity(3, 128, 3, 2, (2, 3, 64, 64), precision=prec, tol_out=tol_out, tol_grad=tol_grad,
+                    fragile_thr=FRAGILE[prec], inv_tol=INV_TOL[prec])
+
+
+def test_tc_rejects_unsupported_shapes_loudly():
+    RB = inb200.ResidualBlock(2, 32, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
+    with pytest.raises(inb200.InbError, match="n_hidden"):
+        RB.forward(g(torch.randn(1, 2, 16, 16)))
+    RB = inb200.ResidualBlock(2, 128, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
+    with pytest.raises(inb200.InbError, match="tiled"):
+        RB.forward(g(torch.randn(1, 2, 12, 12)))
