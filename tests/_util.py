@@ -53,8 +53,8 @@ class FragileUnits:
     while the float64 oracle runs its backward.  At such a unit _relugrad (activation_functions.jl:84)
     is discontinuous: ANY arithmetic that is not bit-identical (the reference's own fp32 on another
     BLAS included) may take the other branch, and the gradient then differs by O(1) around that unit.
-    Parity of gradients is therefore asserted strictly when no unit is fragile, and through the median
-    elementwise error when the oracle itself reports fragile units (assert_grad_close)."""
+    Parity of gradients is therefore asserted strictly when no unit is fragile, and with the bound
+    TOL_GRAD_FRAGILE when the oracle itself reports fragile units (assert_grad_close)."""
 
     def __init__(self, thr):
         self.thr, self.count, self.total = thr, 0, 0
@@ -74,20 +74,17 @@ class FragileUnits:
         O.relu_grad = self._orig
 
 
-def median_err(a, b):
-    """median elementwise |a - b| relative to rms(b): insensitive to the few elements a flipped unit touches"""
-    a = a.detach().double().cpu().reshape(-1)
-    b = b.detach().double().cpu().reshape(-1)
-    return ((a - b).abs().median() / b.pow(2).mean().sqrt()).item()
+# gradient bound that applies ONLY when the float64 oracle reports fragile ReLU units for the arithmetic
+# under test: a unit that takes the other branch of _relugrad perturbs the gradients it feeds by O(1)
+# (a flipped unit behind the 1x1 conv reaches every hidden channel of its pixel), so the L2 error is then
+# set by the number of flips, not by the arithmetic.  Strict, flip-free gradient parity of the same
+# kernels is asserted by test_resblock_exact_lattice and by every float32-path test.
+TOL_GRAD_FRAGILE = 2e-2
 
 
 def assert_grad_close(a, b, tol, fragile, what=""):
-    """strict relative-L2 parity; when the float64 oracle itself reports fragile ReLU units the strict
-    bound may be missed around those units only: then the median elementwise error must still meet
-    `tol` (a systematic error would move every element) and the L2 error stays below 5e-2."""
     r = rel(a, b)
     if r < tol:
         return
     assert fragile is not None and fragile.count > 0, f"{what}: {r} >= {tol} and no fragile ReLU unit explains it"
-    med = median_err(a, b)
-    assert med < tol and r < 5e-2, f"{what}: rel {r}, median {med} (fragile ReLU units: {fragile.count}/{fragile.total})"
+    assert r < max(TOL_GRAD_FRAGILE, tol), f"{what}: rel {r} (fragile ReLU units: {fragile.count}/{fragile.total})"

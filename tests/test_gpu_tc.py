@@ -104,3 +104,36 @@ def test_tc_rejects_unsupported_shapes_loudly():
     RB = inb200.ResidualBlock(2, 128, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
     with pytest.raises(inb200.InbError, match="tiled"):
         RB.forward(g(torch.randn(1, 2, 12, 12)))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("sp", [(16, 16), (8, 8, 8)])
+def test_resblock_exact_lattice(prec, sp):
+    """Flip-free gradient parity: inputs and weights on an integer lattice with half-integer biases, so
+    every pre-activation is exactly representable, never zero-ambiguous, and every sum is exact in fp32
+    accumulation (and in the hi/lo bf16 split, whose dropped lo*lo term vanishes because one operand of
+    every product has an empty lo part).  Forward, dX and all five parameter gradients must then equal
+    the float64 oracle to rounding of the final sums only - no tolerance for ReLU-mask flips is needed."""
+    gen = torch.Generator().manual_seed(17)
+    B, Cin, nh, Cout = 2, 6, 128, 12
+    nd = len(sp)
+
+    def tern(shape, density):
+        v = torch.randint(-1, 2, shape, generator=gen).float()
+        return v * (torch.rand(shape, generator=gen) < density).float()
+    RB = inb200.ResidualBlock(Cin, nh, n_out=Cout, k1=3, k2=1, p1=1, p2=0, ndims=nd, precision=prec, device=DEV)
+    W = [tern((nh, Cin) + (3,) * nd, 0.3), tern((nh, nh) + (1,) * nd, 0.05), tern((nh, Cout) + (3,) * nd, 0.05 if nd == 2 else 0.02),
+         torch.full((nh,), 0.5), torch.full((nh,), 0.25)]
+    for p, w in zip(RB.get_params(), W):
+        p.data.copy_(w)
+    R64 = O.ResidualBlock(*[w.double() for w in W], p1=1, p2=0)
+    X = torch.randint(-1, 2, (B, Cin) + sp, generator=gen).float()
+    dY = torch.randint(-1, 2, (B, Cout) + sp, generator=gen).float()
+    Y1, Y2, _ = R64.forward(X.double(), save=True)
+    assert (Y1.abs() >= 0.25).all() and (Y2.abs() >= 0.25).all()  # no unit anywhere near the ReLU kink
+    assert rel(RB.forward(g(X)), R64.forward(X.double())) < 1e-7
+    dX = RB.backward(g(dY), g(X))
+    dX64 = R64.backward(dY.double(), X.double())
+    assert rel(dX, dX64) < 1e-7
+    for name, p, q in zip("W1 W2 W3 b1 b2".split(), RB.get_params(), R64.params()):
+        assert rel(p.grad, q.grad) < 1e-6, f"{name} {rel(p.grad, q.grad)}"
