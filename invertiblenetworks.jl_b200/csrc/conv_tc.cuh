@@ -29,7 +29,9 @@ bool tc_geometry_ok(const Geo& g, int B);
 void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_bs, int c0, const float* in1,
                    long long in1_bs, int Cin, int cpad, Planes out);
 // reference weight (C order w[d0][d1][T]) -> planes [npad][T*cpad] (K-major rows), mode PACK_CONV/PACK_DATA
-void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int cpad, Planes out);
+// add_identity: add 1 on the diagonal of the centre tap (folds the block's residual skip into conv2 / dgrad2)
+void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int cpad, Planes out,
+                  int add_identity = 0);
 // per-channel sum over rows of planes [M][C] -> out[C] (bias gradients)
 void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out);
 
@@ -47,7 +49,6 @@ struct ConvTcSpec {
   int mode;
   Planes out;
   int relu_encode;
-  Planes skip;    // added (hi+lo), nullable
   Planes mask;    // sign bit of hi -> zero the value, nullable
   // mode 1: fp32 (B,C,px) output
   float* out0; long long out0_bs; int n0;

@@ -177,7 +177,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
   Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, T2 * nh), W3 = planes_new(c, cout_pad, T1 * nh);
   op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
-  op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2);
+  op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
   op_pack_w_tc(c, PACK_DATA, nh, s.Cout, T1, p.W3, cout_pad, nh, W3);
   {  // X2 = relu(conv(X, W1) + b1)                           layer_residual_block.jl:122-123
     ConvTcSpec cs = tc_base(s);
@@ -188,7 +188,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   {  // X3 = relu(X2 + conv(X2, W2) + b2)                      :125-126
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k2; cs.in = H1; cs.cpad_in = nh; cs.w = W2; cs.N = nh; cs.n_real = nh; cs.bias = p.b2;
-    cs.mode = 0; cs.out = H2; cs.relu_encode = 1; cs.skip = H1;
+    cs.mode = 0; cs.out = H2; cs.relu_encode = 1;
     op_conv_tc(c, cs);
   }
   {  // Y3 = \nabla conv_data(X3, W3)                           :128-129
@@ -231,10 +231,10 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
   }
   {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
     Planes W = wview(nh, T2 * nh);
-    op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W);
+    op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W, 1);  // + I: the '+ dY2' of :155
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k2; cs.in = G2; cs.cpad_in = nh; cs.w = W; cs.N = nh; cs.n_real = nh;
-    cs.mode = 0; cs.out = G1; cs.skip = G2; cs.mask = H1;
+    cs.mode = 0; cs.out = G1; cs.mask = H1;
     op_conv_tc(c, cs);
   }
   {  // dW2 = \nabla conv_filter(X2, dY2); db2 = sum dY2         :156-157

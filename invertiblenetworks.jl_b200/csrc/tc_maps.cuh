@@ -1,0 +1,11 @@
+// tc_maps.cuh - host-side TMA tensor-map builders shared by the tensor-core kernels (conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include "conv_tc.cuh"
+
+namespace inb {
+// pixel-major activation planes [B][D][H][W][pitch] bf16, box (ck channels, tile box), swizzle = ck*2 bytes
+CUtensorMap make_act_map(const __nv_bfloat16* base, int pitch, const Geo& g, int B, int ck, const TileBox& tb);
+// weight planes [rows][ktot] bf16 (K-major rows), box (ck, rows)
+CUtensorMap make_w_map(const __nv_bfloat16* base, int ktot, int rows, int ck);
+}  // namespace inb

@@ -10,7 +10,7 @@ import inb200
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-TOL_BF16 = 1e-1   # single-pass bf16 operands (8-bit mantissa), fp32 accumulate; ReLU-mask flips dominate the backward error
+TOL_BF16 = 1.5e-1   # single-pass bf16 operands (8-bit mantissa), fp32 accumulate; ReLU-mask flips dominate the backward error
 TOLS = {"bf16x3": (TOL_OUT, TOL_GRAD), "bf16": (TOL_BF16, 2 * TOL_BF16)}
 # a ReLU unit is "fragile" when its pre-activation is closer to zero than the arithmetic's own error
 FRAGILE = {"bf16x3": 1e-4, "bf16": 3e-2}
