@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("INB_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("INB_PRECISION", "bf16x3"))
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--global-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -97,7 +97,7 @@ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 enum Family {
   F_SQUEEZE = 0, F_COPY, F_AN_STATS, F_AN_HH_FWD, F_HH_AN_INV, F_HH_AN_BWD, F_GRAD_FINISH, F_COUPLING_FWD,
   F_COUPLING_INV, F_COUPLING_BWD, F_PACK, F_CONV_SIMT, F_WGRAD_SIMT, F_CHANNEL_SUM, F_NLL, F_MISC,
-  F_CONV_TC, F_WGRAD_TC, F_LAYOUT_TC, F_COUNT
+  F_CONV_TC, F_WGRAD_TC, F_LAYOUT_TC, F_COL2IM, F_COUNT
 };
 struct Prof {
   cudaStream_t st;

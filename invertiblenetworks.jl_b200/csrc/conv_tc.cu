@@ -68,6 +68,19 @@ CUtensorMap make_w_map(const __nv_bfloat16* base, int ktot, int rows, int ck) {
   return m;
 }
 
+CUtensorMap make_rows_map(const __nv_bfloat16* base, int pitch, long long rows, int box_c, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(2, "cuTensorMapEncodeTiled(rows) failed with %d", (int)r);
+  return m;
+}
+
 TileBox make_tile_box(const Geo& g, int B, int P) {
   TileBox t{1, 1, 1, 1, false};
   int rem = P;
@@ -184,7 +197,7 @@ __global__ void k_colsum_tc(const uint32_t* __restrict__ hi, const uint32_t* __r
   const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
   float s0 = 0.f, s1 = 0.f;
   for (long long r = r0 + rl; r < r1; r += nrl) {
-    uint32_t h = hi[r * C2 + cp], l = lo[r * C2 + cp];
+    const uint32_t h = hi[r * C2 + cp], l = lo ? lo[r * C2 + cp] : 0u;
     s0 += bf16lo_to_f(h) + bf16lo_to_f(l);
     s1 += bf16hi_to_f(h) + bf16hi_to_f(l);
   }
@@ -200,7 +213,8 @@ void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out) {
   const int threads = (256 / C2) * C2 > 0 ? (256 / C2) * C2 : C2;
   long long blocks = std::min<long long>(cdiv(M, 64), 148 * 4);
   long long rpb = cdiv(M, blocks);
-  k_colsum_tc<<<(unsigned)cdiv(M, rpb), threads, 0, c.st>>>((const uint32_t*)in.hi, (const uint32_t*)in.lo, M, C2, rpb, out);
+  // single-pass bf16 keeps only the hi planes
+  k_colsum_tc<<<(unsigned)cdiv(M, rpb), threads, 0, c.st>>>((const uint32_t*)in.hi, c.prec == 1 ? (const uint32_t*)in.lo : nullptr, M, C2, rpb, out);
   INB_CUDA(cudaGetLastError());
 }
 

@@ -70,4 +70,29 @@ struct WgradTcSpec {
 };
 void op_wgrad_tc(Ctx& c, const WgradTcSpec& s);
 
+// Fused pass of the block's three contractions (conv_tc_chain.cu): im2col-GEMM -> per-pixel GEMM ->
+// tap-expanded GEMM + col2im.  mode 0 = forward (bias + ReLU epilogues), mode 1 = backward (relu-grad masks).
+struct ChainSpec {
+  Geo g;
+  int B;
+  int k1;
+  int nh;
+  Planes in;          // [M][cin_pad], pitch a multiple of 16
+  Planes w1, w2, w3;  // [nh][T*cin_pad], [nh][nh] (+I), tap-expanded [n3pad][nh]
+  int Cn;             // real output channels of the last contraction
+  int mode;
+  const float *bias1, *bias2;
+  Planes mask1, mask2;
+  Planes o1, o2;      // hidden outputs in HBM (hi == nullptr: not stored)
+  float* P;           // scratch [M][chain_n3pad(taps, Cn)]
+  // output of col2im, same meaning as ConvTcSpec mode 1
+  float* out0; long long out0_bs; int n0;
+  float* out1; long long out1_bs; int out1_accum;
+  const float* add; long long add_bs; int add_n;
+};
+int chain_n3pad(int taps, int Cn);
+bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int c_in_pad, int Cn);
+void op_pack_wexp_tc(Ctx& c, int nh, int Cn, int T, const float* w, int n3pad, Planes out);
+void op_rb_chain(Ctx& c, const ChainSpec& s);
+
 }  // namespace inb

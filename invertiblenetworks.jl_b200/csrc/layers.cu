@@ -175,6 +175,26 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
   size_t m = c.ar->mark();
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
+  if (chain_supported(s.g, s.B, s.k1, s.k2, nh, cin_pad, s.Cout)) {
+    // one fused kernel for the three contractions (conv_tc_chain.cu); the hidden tensors reach HBM only
+    // when a backward pass follows (h.G != nullptr: the recompute of flow_backward)
+    const int n3pad = chain_n3pad(T1, s.Cout);
+    Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
+    op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
+    op_pack_w_tc(c, PACK_CONV, nh, nh, 1, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
+    op_pack_wexp_tc(c, nh, s.Cout, T1, p.W3, n3pad, W3);
+    ChainSpec cs{};
+    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
+    cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
+    cs.mode = 0; cs.bias1 = p.b1; cs.bias2 = p.b2;
+    if (h.G) { cs.o1 = H1; cs.o2 = H2; }
+    cs.P = c.ar->f32((size_t)M * n3pad);
+    cs.out0 = Y3; cs.out0_bs = (long long)s.Cout * px; cs.n0 = s.Cout;
+    cs.add_n = 1 << 30;
+    op_rb_chain(c, cs);
+    c.ar->release(m);
+    return;
+  }
   Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, T2 * nh), W3 = planes_new(c, cout_pad, T1 * nh);
   op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
   op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
@@ -212,10 +232,31 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
   Planes G1 = H2;  // dY1 reuses X3's storage once dW3 and the dgrad3 mask have consumed it
   Planes dY3p = planes_new(c, M, cout_pad);
   op_nchw_to_tc(c, s.g, s.B, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, cout_pad, dY3p);
+  const bool chain = chain_supported(s.g, s.B, s.k1, s.k2, nh, cout_pad, Cin);
+  if (chain) {
+    // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the
+    // weight gradients below, so dY1 needs its own buffer here
+    G1 = planes_new(c, M, nh);
+    const int n3pad = chain_n3pad(T1, Cin);
+    Planes W3c = planes_new(c, nh, T1 * cout_pad), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
+    op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W3c);   // :151
+    op_pack_w_tc(c, PACK_DATA, nh, nh, 1, p.W2, nh, nh, W2d, 1);         // :155, + I: the '+ dY2'
+    op_pack_wexp_tc(c, nh, Cin, T1, p.W1, n3pad, W1e);                   // :162
+    ChainSpec cs{};
+    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
+    cs.in = dY3p; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
+    cs.mode = 1; cs.mask1 = H2; cs.mask2 = H1;                           // :154, :161
+    cs.o1 = G2; cs.o2 = G1;
+    cs.P = c.ar->f32((size_t)M * n3pad);
+    cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;
+    cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
+    cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
+    op_rb_chain(c, cs);
+  }
   const int kmax = std::max(T1 * std::max(cout_pad, nh), T2 * nh);
   Planes Wp = planes_new(c, std::max(nh, cin_pad), kmax);
   auto wview = [&](int rows, int k) { return planes_at(Wp.hi, rows, k); };
-  {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
+  if (!chain) {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
     Planes W = wview(nh, T1 * cout_pad);
     op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W);
     ConvTcSpec cs = tc_base(s);
@@ -229,7 +270,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     ws.dw = gr.W3;
     op_wgrad_tc(c, ws);
   }
-  {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
+  if (!chain) {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
     Planes W = wview(nh, T2 * nh);
     op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W, 1);  // + I: the '+ dY2' of :155
     ConvTcSpec cs = tc_base(s);
@@ -244,7 +285,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     op_wgrad_tc(c, ws);
     op_colsum_tc(c, M, nh, G2, gr.b2);
   }
-  {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
+  if (!chain) {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
     Planes W = wview(cin_pad, T1 * nh);
     op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, W);
     ConvTcSpec cs = tc_base(s);

@@ -11,7 +11,7 @@ namespace inb {
 static const char* kFamilyNames[F_COUNT] = {
     "squeeze", "copy", "actnorm_stats", "actnorm_hh_fwd", "hh_actnorm_inv", "hh_actnorm_bwd", "grad_finish",
     "coupling_fwd", "coupling_inv", "coupling_bwd", "pack_weights", "conv_simt", "wgrad_simt", "channel_sum",
-    "nll_grad", "misc", "conv_tc", "wgrad_tc", "layout_tc"};
+    "nll_grad", "misc", "conv_tc", "wgrad_tc", "layout_tc", "col2im"};
 
 struct Pending {
   cudaEvent_t a, b;

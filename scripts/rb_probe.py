@@ -16,3 +16,10 @@ for _ in range(5):
     Y = RB.forward(X); dX = RB.backward(dY, X)
 e1.record(); torch.cuda.synchronize()
 print("rb fwd+bwd ms", e0.elapsed_time(e1) / 5)
+L = inb200.lib.load(); L.inb_prof_reset(); L.inb_prof_enable(1)
+for _ in range(3):
+    Y = RB.forward(X); dX = RB.backward(dY, X)
+torch.cuda.synchronize(); L.inb_prof_enable(0)
+for r in sorted(inb200.lib.prof_table(), key=lambda r: -r["ms"]):
+    print(f"  {r['name']:16s} {r['ms']/3:8.3f} ms/iter  launches/iter {r['launches']/3:5.1f}  "
+          f"{(r['flops']/r['ms']/1e9 if r['ms'] else 0):8.1f} TF/s  {(r['bytes']/r['ms']/1e6 if r['ms'] else 0):8.1f} GB/s")
