@@ -169,6 +169,9 @@ int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, voi
  * and its algorithmic flops / bytes are summed; inb_prof_get synchronises on the recorded events. */
 long long inb_launch_count(void);
 int inb_prof_enable(int on);
+/* diagnostics: device buffer of 16 x 16 int64 that receives per-tile phase timestamps (SM clock) of CTA 0 of the
+   fused ResidualBlock kernel (MMA issuer: slots 0-5, first epilogue warp: slots 6-11); NULL switches it off */
+int inb_debug_chain_trace(void* dev_buf);
 int inb_prof_reset(void);
 int inb_prof_num(void);
 int inb_prof_get(int index, char* name, int name_len, long long* launches, long long* scopes, double* ms,

@@ -81,6 +81,20 @@ CUtensorMap make_rows_map(const __nv_bfloat16* base, int pitch, long long rows, 
   return m;
 }
 
+// fp32 [rows][pitch] tensor, box (box_c <= 32 columns = 128 bytes, box_rows), SWIZZLE_128B (P of the fused chain)
+CUtensorMap make_rows_map_f32(const float* base, int pitch, long long rows, int box_c, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(2, "cuTensorMapEncodeTiled(fp32 rows) failed with %d", (int)r);
+  return m;
+}
+
 TileBox make_tile_box(const Geo& g, int B, int P) {
   TileBox t{1, 1, 1, 1, false};
   int rem = P;
@@ -151,6 +165,95 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
   const long long M = g.px * B;
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * Cin + 4.0 * cpad) * M);
   k_nchw_to_tc<<<(unsigned)cdiv(M, 256), 256, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, Cin, cpad, g.px, M, out.hi, out.lo);
+  INB_CUDA(cudaGetLastError());
+}
+
+// im2col of a (B,C,px) fp32 tensor [two sources, conditional cat] into pixel-major bf16 hi/lo rows
+//   col[m][tap*C + c] = x[c][pix(m) + off(tap)]   (zero outside the image = the conv's zero padding),
+// K padded with zeros to kp (multiple of 64) except column `ones_col` (>= 0), which is 1.0: the bias gradient
+// then falls out of the weight-gradient MMA as one more column.  thread = (pixel, group of 8 columns)
+__global__ void k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
+                            long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M,
+                            int kp, int ones_col, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int groups = kp / 8;
+  const long long total = M * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long m = i / groups;
+    const long long b = m / px, pix = m - b * px;
+    long long t = pix;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
+    const int z = (int)t;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 hh[2], ll[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = gidx * 8 + 2 * j + u;
+        float v = 0.f;
+        if (k < T * C) {
+          const int tap = k / C, ch = k - tap * C;
+          int dx = 0, dy = 0, dz = 0;
+          if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) {
+            const long long q = ((long long)zz * H + yy) * W + xx;
+            v = (ch < c0) ? __ldg(in0 + b * in0_bs + (long long)ch * px + q)
+                          : __ldg(in1 + b * in1_bs + (long long)(ch - c0) * px + q);
+          }
+        } else if (k == ones_col) {
+          v = 1.f;
+        }
+        split_bf16(v, hh[u], ll[u]);
+      }
+      h[j] = pack2(hh[0], hh[1]);
+      l[j] = pack2(ll[0], ll[1]);
+    }
+    *reinterpret_cast<uint4*>(hi + m * kp + gidx * 8) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + m * kp + gidx * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
+                  long long in1_bs, int C, int kp, int ones_col, Planes out) {
+  if (c.dry()) return;
+  const long long M = g.px * B;
+  const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
+  Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
+  const long long total = M * (kp / 8);
+  k_im2col_tc<<<(unsigned)std::min<long long>(cdiv(total, 256), 148 * 32), 256, 0, c.st>>>(
+      in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M, kp, ones_col, out.hi, out.lo);
+  INB_CUDA(cudaGetLastError());
+}
+
+// dense-K weight rows for the im2col operand: out[n][tap*Cc + cc] (zero up to kp), same values as k_pack_w_tc
+__global__ void k_pack_w_dense_tc(int mode, int d0, int d1, int T, const float* __restrict__ w, int npad, int kp,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long n_el = (long long)npad * kp;
+  const int O = mode == PACK_CONV ? d0 : d1, Cc = mode == PACK_CONV ? d1 : d0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_el;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kp);
+    const int n = (int)(i / kp);
+    float v = 0.f;
+    if (n < O && k < T * Cc) {
+      const int tap = k / Cc, cc = k - tap * Cc;
+      if (mode == PACK_CONV) v = w[((long long)n * d1 + cc) * T + (T - 1 - tap)];
+      else v = w[((long long)cc * d1 + n) * T + tap];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+void op_pack_w_dense_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int kp, Planes out) {
+  if (c.dry()) return;
+  const long long n = (long long)npad * kp;
+  Prof pf(c, F_PACK, 1, 0, 8.0 * n);
+  k_pack_w_dense_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(mode, d0, d1, T, w, npad, kp, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
 }
 

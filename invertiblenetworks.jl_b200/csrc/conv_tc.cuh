@@ -32,6 +32,12 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
 // add_identity: add 1 on the diagonal of the centre tap (folds the block's residual skip into conv2 / dgrad2)
 void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int cpad, Planes out,
                   int add_identity = 0);
+// im2col rows for the fused chain's first GEMM and for the weight gradients (conv_tc.cu: k_im2col_tc):
+// out [M][kp] with kp = chain_kpad(T*C); `ones_col` (>= 0) is a column of ones
+void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
+                  long long in1_bs, int C, int kp, int ones_col, Planes out);
+// weights against those rows: out [npad][kp], column tap*Cc + cc
+void op_pack_w_dense_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int kp, Planes out);
 // per-channel sum over rows of planes [M][C] -> out[C] (bias gradients)
 void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out);
 
@@ -77,8 +83,8 @@ struct ChainSpec {
   int B;
   int k1;
   int nh;
-  Planes in;          // [M][cin_pad], pitch a multiple of 16
-  Planes w1, w2, w3;  // [nh][T*cin_pad], [nh][nh] (+I), tap-expanded [n3pad][nh]
+  Planes in;          // im2col rows [M][kp], pitch = kp (multiple of 64)
+  Planes w1, w2, w3;  // [nh][kp], [nh][nh] (+I), tap-expanded [n3pad][nh]
   int Cn;             // real output channels of the last contraction
   int mode;
   const float *bias1, *bias2;
@@ -91,8 +97,10 @@ struct ChainSpec {
   const float* add; long long add_bs; int add_n;
 };
 int chain_n3pad(int taps, int Cn);
-bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int c_in_pad, int Cn);
+int chain_kpad(int taps, int C, int extra);  // im2col width: taps*C (+ extra columns) rounded up to 64
+bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn);
 void op_pack_wexp_tc(Ctx& c, int nh, int Cn, int T, const float* w, int n3pad, Planes out);
 void op_rb_chain(Ctx& c, const ChainSpec& s);
+void chain_set_trace(long long* p);
 
 }  // namespace inb

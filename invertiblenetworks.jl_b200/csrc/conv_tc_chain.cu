@@ -3,13 +3,13 @@
 // Forward  (layer_residual_block.jl:122-129):  X -> relu(conv(X,W1)+b1) -> relu((W2+I) X2 + b2) -> \nabla conv_data(X3, W3)
 // Backward (layer_residual_block.jl:151-162):  dY3 -> relugrad(conv(dY3,W3),Y2) -> relugrad((W2+I)^T dY2,Y1) -> \nabla conv_data(dY1, W1)
 //
-// Both are  im2col-GEMM (K = taps*16k)  ->  per-pixel GEMM (K = nh)  ->  per-pixel GEMM with TAP-EXPANDED
+// Both are  im2col-GEMM (K = taps*C)  ->  per-pixel GEMM (K = nh)  ->  per-pixel GEMM with TAP-EXPANDED
 // output columns (N = taps*Cn) followed by a col2im gather (k_col2im): \nabla conv_data IS "GEMM, then
 // col2im", so the 3x3 stencil of the last contraction costs one read of its 256-channel operand instead
 // of nine, and every hidden tensor stays on the SM:
 //
-//   GEMM1: A = nine 5-D TMA boxes of the (padded, bf16 hi/lo) input shifted by the tap (zero fill = padding),
-//          D1[128 x nh] in TMEM columns R0
+//   GEMM1: A = im2col rows [M][taps*C -> 64k] of the block input (bf16 hi/lo, k_im2col_tc), D1[128 x nh] in
+//          TMEM columns R0
 //   E1   : tcgen05.ld -> +bias, ReLU (sign bit of -0.0 keeps the _relugrad mask) | relu-grad masking ->
 //          bf16 hi/lo -> shared memory in the K-major SWIZZLE_128B operand layout, 64-channel chunk by chunk
 //   GEMM2: A = those chunks as they become ready, B = (W2 + I) streamed through the TMA ring, D2 in R1
@@ -32,27 +32,28 @@ namespace inb {
 using namespace tc;
 
 struct ChainMaps {
-  CUtensorMap A[2], W1[2], W2[2], W3a[2], W3b[2], O1[2], O2[2];
+  CUtensorMap A[2], W1[2], W2[2], W3[2], O1[2], O2[2], P;
 };
 
 struct ChainArgs {
   int W, H, D;
   long long M;
   int ntiles;
-  int taps1, ksz1, nch1;  // GEMM1 k-blocks: taps1 x nch1 blocks of 16 channels
+  int nkb1;               // GEMM1 k-blocks of 64 im2col columns
   int nh, nchunk;         // hidden channels (128 | 256), nh / 64
-  int n3a, n3b, n3pad;    // GEMM3 column parts (multiples of 16, <= 256) and the pitch of P
+  int n3a, n3b, n3pad;    // GEMM3 columns in R0 / R1 and the pitch of P (multiple of 16)
+  int np3;                // 128-column pieces of GEMM3
   int stages;
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
   const __nv_bfloat16 *mask1, *mask2;  // hi planes [M][nh] whose sign bits are the masks of E1 / E2
   float* P;
+  long long* trace;       // diagnostics: per-tile phase timestamps of CTA 0 (inb_debug_chain_trace), nullable
 };
 
 constexpr int kChainThreads = 352;
 constexpr uint32_t kPlane = 16384;      // one plane of a 128 x 64 chunk / of a weight k-block
-constexpr uint32_t kATap = 4096;        // 128 pixels x 16 channels
 
 __device__ __forceinline__ void chain_tap_offset(int tap, int ksz, int D, int& dx, int& dy, int& dz) {
   if (ksz == 1) { dx = dy = dz = 0; return; }
@@ -65,14 +66,20 @@ __device__ __forceinline__ void chain_tap_offset(int tap, int ksz, int D, int& d
 template <int MODE, int NT>
 __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint4 mh, uint4& oh, uint4& ol) {
   const uint32_t mm[4] = {mh.x, mh.y, mh.z, mh.w};
+  float bias[8];
+  if (MODE == 0) {
+    const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
     uint32_t sign = 0;
     if (MODE == 0) {
-      a += sb[2 * j];
-      b += sb[2 * j + 1];
+      a += bias[2 * j];
+      b += bias[2 * j + 1];
       // relu(x) = 0 is stored as -0.0 when x < 0: the sign bit of the hi plane is the _relugrad mask
       sign = ((__float_as_uint(a) >> 16) & 0x8000u) | (__float_as_uint(b) & 0x80000000u);
       a = fmaxf(a, 0.f);
@@ -102,8 +109,6 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
   constexpr uint32_t CHUNK = NP * kPlane;        // hi (+ lo) of one 128 x 64 chunk
   constexpr uint32_t STAGE = NP * kPlane;        // one ring stage
-  constexpr uint32_t W1OFF = NP * kATap;         // weights of a GEMM1 k-block follow the A planes
-  constexpr uint32_t W1PLANE = (NT == 1) ? 8192 : 8192;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* hbuf = smem;
   uint8_t* ring = hbuf + (size_t)a.nchunk * CHUNK;
@@ -114,7 +119,7 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   uint64_t* stdone = hready + 4;  // [4]
   uint64_t* e3done = stdone + 4;  // [1]
   uint32_t* tslot = reinterpret_cast<uint32_t*>(e3done + 1);
-  float* sbias = reinterpret_cast<float*>(tslot + 2);  // [2][256]
+  float* sbias = reinterpret_cast<float*>(tslot + 4);  // [2][256], 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -122,13 +127,13 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     prefetch_tmap(&maps.A[0]);
     prefetch_tmap(&maps.W1[0]);
     prefetch_tmap(&maps.W2[0]);
-    prefetch_tmap(&maps.W3a[0]);
+    prefetch_tmap(&maps.W3[0]);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
       for (int s = 0; s < 3; ++s) mbar_init(dfull + s, 1);
-      for (int s = 0; s < 4; ++s) { mbar_init(hready + s, 256); mbar_init(stdone + s, 1); }
+      for (int s = 0; s < 4; ++s) { mbar_init(hready + s, 8); mbar_init(stdone + s, 1); }
       mbar_init(e3done, 8);
       fence_barrier_init();
     }
@@ -145,11 +150,11 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
-  const int nkb1 = a.taps1 * a.nch1;
-  const int nkb2 = a.nh / 32;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    // every box is [<=128 rows] x [64 bf16 = 128 bytes]: the TMA unit is request-rate bound (a 32-byte row costs
+    // what a 128-byte one does), which is why the first GEMM reads im2col rows instead of nine shifted 32-byte taps
     if (elect_one()) {
       uint32_t it = 0;
       auto acquire = [&](uint32_t tx) -> uint8_t* {
@@ -160,41 +165,35 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         return ring + (size_t)s * STAGE;
       };
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        long long t = (long long)tile * 128;
-        const int x0 = (int)(t % a.W); t /= a.W;
-        const int y0 = (int)(t % a.H); t /= a.H;
-        const int z0 = (int)(t % a.D); t /= a.D;
-        const int b0 = (int)t;
-        for (int kb = 0; kb < nkb1; ++kb, ++it) {
-          const int tap = kb / a.nch1, ch = kb - tap * a.nch1;
-          int dx, dy, dz;
-          chain_tap_offset(tap, a.ksz1, a.D, dx, dy, dz);
-          uint8_t* st = acquire(NP * (kATap + a.nh * 32));
-          uint64_t* fb = full + it % a.stages;
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
-            tma_load_5d(&maps.A[pl], fb, st + pl * kATap, ch * 16, x0 + dx, y0 + dy, z0 + dz, b0);
-            tma_load_2d(&maps.W1[pl], fb, st + W1OFF + pl * W1PLANE, kb * 16, 0);
-          }
-        }
-        for (int kb = 0; kb < nkb2; ++kb, ++it) {
-          uint8_t* st = acquire(NP * a.nh * 64);
-          uint64_t* fb = full + it % a.stages;
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W2[pl], fb, st + pl * kPlane, kb * 32, 0);
-        }
-        for (int kb = 0; kb < nkb2; ++kb, ++it) {
-          uint8_t* st = acquire(NP * a.n3a * 64);
-          uint64_t* fb = full + it % a.stages;
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W3a[pl], fb, st + pl * kPlane, kb * 32, 0);
-        }
-        if (a.n3b) {
-          for (int kb = 0; kb < nkb2; ++kb, ++it) {
-            uint8_t* st = acquire(NP * a.n3b * 64);
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          {  // 128 pixels x 64 im2col columns (rows beyond M are zero-filled)
+            uint8_t* st = acquire(NP * kPlane);
             uint64_t* fb = full + it % a.stages;
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W3b[pl], fb, st + pl * kPlane, kb * 32, a.n3a);
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.A[pl], fb, st + pl * kPlane, kb * 64, tile * 128);
+            ++it;
+          }
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W1[pl], fb, st + pl * kPlane, kb * 64, nhf * 128);
+          }
+        }
+        for (int c = 0; c < a.nchunk; ++c) {
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W2[pl], fb, st + pl * kPlane, c * 64, nhf * 128);
+          }
+        }
+        for (int pc = 0; pc < a.np3; ++pc) {
+          for (int c = 0; c < a.nchunk; ++c, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W3[pl], fb, st + pl * kPlane, c * 64, pc * 128);
           }
         }
       }
@@ -202,84 +201,85 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc_h = make_idesc_bf16(128, a.nh, 0, 0);
-      const uint32_t idesc_a = make_idesc_bf16(128, a.n3a, 0, 0);
-      const uint32_t idesc_b = make_idesc_bf16(128, a.n3b ? a.n3b : 16, 0, 0);
+      const uint32_t idesc_2 = make_idesc_bf16(128, 128, 0, 0);    // GEMM1 / GEMM2: 128-column halves
       const uint32_t hb = smem_u32(hbuf);
       uint32_t it = 0, tl = 0;
+      long long twait = 0;
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % a.stages;
         const uint32_t ph = (it / a.stages) & 1;
+        const long long t0 = a.trace ? clock64() : 0;
         mbar_wait(full + s, ph);
+        if (a.trace) twait += clock64() - t0;
         tc_fence_after();
         return smem_u32(ring + (size_t)s * STAGE);
       };
-      // one K=32 weight block against k-steps (2j, 2j+1) of chunk c
-      auto chunk_block = [&](uint32_t d_tmem, uint32_t idesc, int c, int j, uint32_t sa, uint32_t& acc) {
+      // K-major SWIZZLE_128B descriptors differ only in the start-address field: the constant high word is built
+      // once and every MMA costs two integer adds (descriptor arithmetic in the single issuing thread was
+      // what paced the tensor pipe before)
+      const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
+      // one [128 rows x 64 k] A block at a_addr against one [<=128 rows x 64 k] B block at b_addr: 4 k-steps x NT terms
+      auto mma_block = [&](uint32_t d_tmem, uint32_t idesc, uint32_t a_addr, uint32_t b_addr, uint32_t first) {
+        const uint32_t alo = (a_addr >> 4) & 0x3FFF, blo = (b_addr >> 4) & 0x3FFF;
 #pragma unroll
         for (int term = 0; term < NT; ++term) {
-          const uint32_t ta = hb + c * CHUNK + ((term == 2) ? kPlane : 0);
-          const uint32_t tb = sa + ((term == 1) ? kPlane : 0);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint64_t ad = make_smem_desc(ta + (2 * j + k) * 32, 0, 1024, LAYOUT_SW128);
-            const uint64_t bd = make_smem_desc(tb + k * 32, 0, 512, LAYOUT_SW64);
-            umma_f16(d_tmem, ad, bd, idesc, acc);
-            acc = 1;
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ((uint64_t)dhi << 32) | (alo + ((term == 2) ? (kPlane >> 4) : 0) + 2 * k);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            umma_f16(d_tmem, ad, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
           }
         }
       };
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tl) {
         const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
+        long long* tr = (a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
+        if (tr) tr[0] = clock64();
         if (a.n3b && tl > 0) {  // D3b of the previous tile lives where D1 goes
           mbar_wait(e3done, (tl - 1) & 1);
           tc_fence_after();
         }
-        uint32_t acc = 0;
-        for (int kb = 0; kb < nkb1; ++kb, ++it) {
-          const uint32_t sa = stage_wait();
-#pragma unroll
-          for (int term = 0; term < NT; ++term) {
-            const uint64_t ad = make_smem_desc(sa + ((term == 2) ? kATap : 0), 0, 256, LAYOUT_SW32);
-            const uint64_t bd = make_smem_desc(sa + W1OFF + ((term == 1) ? W1PLANE : 0), 0, 256, LAYOUT_SW32);
-            umma_f16(R0, ad, bd, idesc_h, acc);
-            acc = 1;
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          const uint32_t sA = stage_wait();
+          const int slotA = it % a.stages;
+          ++it;
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            const uint32_t sb = stage_wait();
+            mma_block(R0 + nhf * 128, idesc_2, sA, sb, kb == 0);
+            umma_commit(empty + it % a.stages);
           }
-          umma_commit(empty + it % a.stages);
+          umma_commit(empty + slotA);  // the im2col block is released after both column halves have read it
         }
         umma_commit(dfull + 0);
-        acc = 0;
+        if (tr) { tr[1] = clock64(); tr[12] = twait; twait = 0; }
         for (int c = 0; c < a.nchunk; ++c) {
           mbar_wait(hready + c, 0);
           tc_fence_after();
-          for (int j = 0; j < 2; ++j, ++it) {
+          if (tr && c == 0) tr[2] = clock64();
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
             const uint32_t sa = stage_wait();
-            chunk_block(R1, idesc_h, c, j, sa, acc);
+            mma_block(R1 + nhf * 128, idesc_2, hb + c * CHUNK, sa, c == 0);
             umma_commit(empty + it % a.stages);
           }
         }
         umma_commit(dfull + 1);
-        acc = 0;
-        for (int c = 0; c < a.nchunk; ++c) {
-          mbar_wait(hready + c, 1);
-          tc_fence_after();
-          for (int j = 0; j < 2; ++j, ++it) {
+        if (tr) { tr[3] = clock64(); tr[13] = twait; twait = 0; }
+        for (int pc = 0; pc < a.np3; ++pc) {
+          const int n = min(128, a.n3pad - pc * 128);
+          const uint32_t idesc_3 = make_idesc_bf16(128, n, 0, 0);
+          const uint32_t dst = (pc < 2) ? (R0 + pc * 128) : (R1 + (pc - 2) * 128);
+          for (int c = 0; c < a.nchunk; ++c, ++it) {
+            mbar_wait(hready + c, 1);  // pieces in R1 come after all of E2 (piece-outer order)
+            tc_fence_after();
+            if (tr && pc == 0 && c == 0) tr[4] = clock64();
             const uint32_t sa = stage_wait();
-            chunk_block(R0, idesc_a, c, j, sa, acc);
+            mma_block(dst, idesc_3, hb + c * CHUNK, sa, c == 0);
             umma_commit(empty + it % a.stages);
           }
         }
-        if (a.n3b) {
-          acc = 0;
-          for (int c = 0; c < a.nchunk; ++c) {
-            for (int j = 0; j < 2; ++j, ++it) {
-              const uint32_t sa = stage_wait();
-              chunk_block(R1, idesc_b, c, j, sa, acc);
-              umma_commit(empty + it % a.stages);
-            }
-          }
-        }
         umma_commit(dfull + 2);
+        if (tr) { tr[5] = clock64(); tr[14] = twait; }
+        twait = 0;
       }
     }
   } else if (warp < 10) {
@@ -294,83 +294,121 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
       const long long m = (long long)tile * 128 + row;
       const bool live = m < a.M;
+      long long* tr = (a.trace && blockIdx.x == 0 && tl < 16 && e == 0 && lane == 0) ? a.trace + tl * 16 + 6 : nullptr;
 #pragma unroll 1
       for (int stg = 0; stg < 2; ++stg) {
-        const uint32_t dsrc = (stg ? R1 : R0) + lane_sel;
-        const float* sb = sbias + stg * 256;
-        const __nv_bfloat16* mk = stg ? a.mask2 : a.mask1;
+        const uint32_t dsrc = (stg ? R1 : R0) + lane_sel + 32 * half;
+        const float* sb = sbias + stg * 256 + 32 * half;
+        const __nv_bfloat16* mk = (stg ? a.mask2 : a.mask1) + m * a.nh + 32 * half;
+        const bool wait_store = a.store && (tl > 0 || stg > 0);
         mbar_wait(dfull + stg, tl & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < a.nchunk; ++c) {
-          const int col = 64 * c + 32 * half;
-          uint4 msk[4];
+        if (stg == 0 && tl > 0) {  // the P stores of the previous tile have read the operand buffer
+          if (e == 0 && lane == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        if (tr) tr[2 * stg] = clock64();
+        // software pipeline over the 64-channel chunks: the TMEM (and mask) loads of chunk c+1 are in flight
+        // while chunk c is converted and written to shared memory
+        uint32_t rA[32], rB[32];
+        uint4 mA[4], mB[4];
+        auto fetch = [&](int c, uint32_t (&r)[32], uint4 (&mm)[4]) {
           if (a.mode == 1) {
-            if (live) {
-              const uint4* mp = reinterpret_cast<const uint4*>(mk + m * a.nh + col);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) msk[j] = __ldg(mp + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) msk[j] = make_uint4(0, 0, 0, 0);
-            }
+            for (int j = 0; j < 4; ++j)
+              mm[j] = live ? __ldg(reinterpret_cast<const uint4*>(mk + 64 * c) + j) : make_uint4(0, 0, 0, 0);
           }
-          uint32_t r[32];
-          tmem_ld32(dsrc + col, r);
-          if (a.store && (tl > 0 || stg > 0)) mbar_wait(stdone + c, stg ^ 1);  // the chunk's previous store has read it
-          tmem_ld_wait();
+          tmem_ld32(dsrc + 64 * c, r);
+        };
+        auto emit = [&](int c, const uint32_t (&r)[32], const uint4 (&mm)[4]) {
+          if (wait_store) mbar_wait(stdone + c, stg ^ 1);  // the chunk's previous TMA store has read it
           uint8_t* dst = hbuf + (size_t)c * CHUNK + row * 128;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 oh, ol;
-            if (a.mode == 0) chain_pack8<0, NT>(r + 8 * g, sb + col + 8 * g, make_uint4(0, 0, 0, 0), oh, ol);
-            else chain_pack8<1, NT>(r + 8 * g, sb, msk[g], oh, ol);
+            if (a.mode == 0) chain_pack8<0, NT>(r + 8 * g, sb + 64 * c + 8 * g, make_uint4(0, 0, 0, 0), oh, ol);
+            else chain_pack8<1, NT>(r + 8 * g, sb, mm[g], oh, ol);
             const uint32_t off = (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst + off) = oh;
             if (NT == 3) *reinterpret_cast<uint4*>(dst + kPlane + off) = ol;
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the MMA / TMA (async proxy)
           tc_fence_before();
-          mbar_arrive(hready + c);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hready + c);
+        };
+        fetch(0, rA, mA);
+#pragma unroll 1
+        for (int c = 0; c < a.nchunk; c += 2) {
+          tmem_ld_wait();
+          fetch(c + 1, rB, mB);
+          emit(c, rA, mA);
+          tmem_ld_wait();
+          if (c + 2 < a.nchunk) fetch(c + 2, rA, mA);
+          emit(c + 1, rB, mB);
         }
+        if (tr) tr[2 * stg + 1] = clock64();
       }
       // E3: tap-expanded columns -> P
       mbar_wait(dfull + 2, tl & 1);
       tc_fence_after();
+      if (tr) tr[4] = clock64();
+      // The operand buffer is free now (GEMM3 has read it): stage the fp32 rows there, 128 columns at a time,
+      // so that P is written with coalesced 16-byte stores (a row per thread straight from registers costs one
+      // memory transaction per lane and was the longest phase of the tile).
+      if (a.store) {
 #pragma unroll 1
-      for (int part = 0; part < 2; ++part) {
-        const int n = part ? a.n3b : a.n3a;
-        if (n == 0) break;
-        const uint32_t dsrc = (part ? R1 : R0) + lane_sel;
-        const int nsplit = ((n / 16 + 1) / 2) * 16;
-        const int cbeg = half ? nsplit : 0, cend = half ? n : nsplit;
-        float* prow = a.P + m * a.n3pad + (part ? a.n3a : 0);
+        for (int c = 0; c < a.nchunk; ++c) mbar_wait(stdone + c, 1);  // the TMA stores of this tile's chunks have read them
+      }
+      const int tid = e * 32 + lane;
+#pragma unroll 1
+      for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
+        const int ncols = min(128, a.n3pad - slab * 128);
+        const uint32_t dsrc = ((slab < 2) ? (R0 + slab * 128) : (R1 + (slab - 2) * 128)) + lane_sel;
+        const int nsplit = ((ncols / 16 + 1) / 2) * 16;
+        const int cbeg = half ? nsplit : 0, cend = half ? ncols : nsplit;
+        if (slab > 0) {  // the previous slab's stores have read the staging area
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        // staging = the TMA store's SWIZZLE_128B box layout: 32-column group g at g*16 KB, 128-byte rows
+        auto stage16 = [&](int col, const uint32_t* r) {
+          uint8_t* g = hbuf + (col >> 5) * kPlane + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = ((col & 31) >> 2) + j;
+            *reinterpret_cast<uint4*>(g + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        };
         int c0 = cbeg;
         for (; c0 + 32 <= cend; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(dsrc + c0, r);
           tmem_ld_wait();
-          if (live) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(prow + c0 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          }
+          stage16(c0, r);
+          stage16(c0 + 16, r + 16);
         }
         if (c0 < cend) {
           uint32_t r[16];
           tmem_ld16(dsrc + c0, r);
           tmem_ld_wait();
-          if (live) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(prow + c0 + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-          }
+          stage16(c0, r);
         }
+        fence_proxy_async();
+        if (tr && slab == 0) tr[16 * 16 + 0 - 6] = clock64();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) {
+          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, hbuf + g * kPlane, slab * 128 + g * 32, tile * 128);
+          bulk_commit();
+        }
+        if (tr && slab == 0) tr[16 * 16 + 1 - 6] = clock64();
       }
+      if (tr) tr[5] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(e3done);
     }
+    if (e == 0 && lane == 0) bulk_wait0();
   } else if (a.store) {
     // ------------------------------------------------------------ TMA store warp
     if (lane == 0) {
@@ -480,22 +518,27 @@ void op_pack_wexp_tc(Ctx& c, int nh, int Cn, int T, const float* w, int n3pad, P
 }
 
 // ---------------------------------------------------------------- host side
+static long long* g_chain_trace = nullptr;
+void chain_set_trace(long long* p) { g_chain_trace = p; }
+
 int chain_n3pad(int taps, int Cn) { return (taps * Cn + 15) / 16 * 16; }
 
-bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int c_in_pad, int Cn) {
+int chain_kpad(int taps, int C, int extra) { return (taps * C + extra + 63) / 64 * 64; }
+
+bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn) {
   if (k2 != 1) return false;
   if (nh != 128 && nh != 256) return false;
-  if (c_in_pad % 16 || c_in_pad > 256) return false;
   const int taps = k1 == 1 ? 1 : (g.nd == 3 ? 27 : 9);
+  if (chain_kpad(taps, C_in, 1) > 1024) return false;
   const int n3 = chain_n3pad(taps, Cn);
   if (n3 > 480 || Cn > 128) return false;
-  return make_tile_box(g, B, 128).ok;
+  (void)B;
+  return true;
 }
 
 void op_rb_chain(Ctx& c, const ChainSpec& s) {
   const int taps = s.k1 == 1 ? 1 : (s.g.nd == 3 ? 27 : 9);
-  INB_CHECK(chain_supported(s.g, s.B, s.k1, 1, s.nh, s.in.pitch, s.Cn), "fused ResidualBlock chain: unsupported shape");
-  const TileBox tb = make_tile_box(s.g, s.B, 128);
+  INB_CHECK(s.in.pitch % 64 == 0 && s.w1.pitch == s.in.pitch, "fused ResidualBlock chain: the im2col width must be a multiple of 64");
   if (c.dry()) return;
   const int NT = (c.prec == 1) ? 3 : 1;
   const int NP = NT == 1 ? 1 : 2;
@@ -503,35 +546,34 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.W = s.g.W; a.H = s.g.H; a.D = s.g.D;
   a.M = s.g.px * s.B;
   a.ntiles = (int)cdiv(a.M, 128);
-  a.taps1 = taps;
-  a.ksz1 = s.k1;
-  a.nch1 = s.in.pitch / 16;
+  a.nkb1 = s.in.pitch / 64;
   a.nh = s.nh;
   a.nchunk = s.nh / 64;
   a.n3pad = chain_n3pad(taps, s.Cn);
-  if (a.n3pad <= 256) { a.n3a = a.n3pad; a.n3b = 0; }
-  else { a.n3a = (a.n3pad / 16 + 1) / 2 * 16; a.n3b = a.n3pad - a.n3a; }
+  a.n3a = std::min(a.n3pad, 256);
+  a.n3b = a.n3pad - a.n3a;
+  a.np3 = (a.n3pad + 127) / 128;
   a.mode = s.mode;
   a.store = (s.o1.hi != nullptr) ? 1 : 0;
   a.bias1 = s.bias1; a.bias2 = s.bias2;
   a.mask1 = s.mask1.hi; a.mask2 = s.mask2.hi;
   a.P = s.P;
+  a.trace = g_chain_trace;
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
   const size_t aux = 32 * 8 + 16 + 512 * 4;
   const size_t cap = 227 * 1024;
   int stages = (int)((cap - aux - a.nchunk * chunk) / stage);
   if (stages > 8) stages = 8;
-  INB_CHECK(stages >= 2, "fused ResidualBlock chain: shared memory does not fit");
+  // the im2col block of GEMM1 stays resident while the nh/128 weight halves stream past it
+  INB_CHECK(stages >= 1 + s.nh / 128, "fused ResidualBlock chain: shared memory does not fit");
   a.stages = stages;
   const size_t smem = a.nchunk * chunk + stages * stage + aux;
   ChainMaps mp{};
   for (int pl = 0; pl < 2; ++pl) {
-    const __nv_bfloat16* in = pl ? s.in.lo : s.in.hi;
-    mp.A[pl] = make_act_map(in, s.in.pitch, s.g, s.B, 16, tb);
-    mp.W1[pl] = make_w_map(pl ? s.w1.lo : s.w1.hi, taps * s.in.pitch, s.nh, 16);
-    mp.W2[pl] = make_w_map(pl ? s.w2.lo : s.w2.hi, s.nh, s.nh, 32);
-    mp.W3a[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 32, a.n3a);
-    mp.W3b[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 32, a.n3b ? a.n3b : 16);
+    mp.A[pl] = make_rows_map(pl ? s.in.lo : s.in.hi, s.in.pitch, a.M, 64, 128);
+    mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, 128);
+    mp.W2[pl] = make_rows_map(pl ? s.w2.lo : s.w2.hi, s.nh, s.nh, 64, 128);
+    mp.W3[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 64, 128);
     if (a.store) {
       mp.O1[pl] = make_rows_map(pl ? s.o1.lo : s.o1.hi, s.nh, a.M, 64, 128);
       mp.O2[pl] = make_rows_map(pl ? s.o2.lo : s.o2.hi, s.nh, a.M, 64, 128);
@@ -540,8 +582,9 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
       mp.O2[pl] = mp.W2[pl];
     }
   }
+  mp.P = make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
   const unsigned grid = (unsigned)std::min(a.ntiles, 148);
-  const double flops = 2.0 * a.M * ((double)taps * s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
+  const double flops = 2.0 * a.M * ((double)s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
   {
     Prof pf(c, F_CONV_TC, 1, flops, 0);
     if (NT == 3) {

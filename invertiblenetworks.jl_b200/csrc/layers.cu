@@ -175,17 +175,20 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
   size_t m = c.ar->mark();
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
-  if (chain_supported(s.g, s.B, s.k1, s.k2, nh, cin_pad, s.Cout)) {
+  if (chain_supported(s.g, s.B, s.k1, s.k2, nh, Cin, s.Cout)) {
     // one fused kernel for the three contractions (conv_tc_chain.cu); the hidden tensors reach HBM only
     // when a backward pass follows (h.G != nullptr: the recompute of flow_backward)
     const int n3pad = chain_n3pad(T1, s.Cout);
-    Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
-    op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
+    const int kp = chain_kpad(T1, Cin, 1);
+    Planes W1 = planes_new(c, nh, kp), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
+    Planes xcol = planes_new(c, M, kp);
+    op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, T1 * Cin, xcol);
+    op_pack_w_dense_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, kp, W1);
     op_pack_w_tc(c, PACK_CONV, nh, nh, 1, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
     op_pack_wexp_tc(c, nh, s.Cout, T1, p.W3, n3pad, W3);
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
-    cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
+    cs.in = xcol; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
     cs.mode = 0; cs.bias1 = p.b1; cs.bias2 = p.b2;
     if (h.G) { cs.o1 = H1; cs.o2 = H2; }
     cs.P = c.ar->f32((size_t)M * n3pad);
@@ -232,19 +235,22 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
   Planes G1 = H2;  // dY1 reuses X3's storage once dW3 and the dgrad3 mask have consumed it
   Planes dY3p = planes_new(c, M, cout_pad);
   op_nchw_to_tc(c, s.g, s.B, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, cout_pad, dY3p);
-  const bool chain = chain_supported(s.g, s.B, s.k1, s.k2, nh, cout_pad, Cin);
+  const bool chain = chain_supported(s.g, s.B, s.k1, s.k2, nh, Cout, Cin);
   if (chain) {
     // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the
     // weight gradients below, so dY1 needs its own buffer here
     G1 = planes_new(c, M, nh);
     const int n3pad = chain_n3pad(T1, Cin);
-    Planes W3c = planes_new(c, nh, T1 * cout_pad), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
-    op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W3c);   // :151
+    const int kp = chain_kpad(T1, Cout, 0);
+    Planes W3c = planes_new(c, nh, kp), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
+    Planes dcol = planes_new(c, M, kp);
+    op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol);
+    op_pack_w_dense_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, kp, W3c);   // :151
     op_pack_w_tc(c, PACK_DATA, nh, nh, 1, p.W2, nh, nh, W2d, 1);         // :155, + I: the '+ dY2'
     op_pack_wexp_tc(c, nh, Cin, T1, p.W1, n3pad, W1e);                   // :162
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
-    cs.in = dY3p; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
+    cs.in = dcol; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
     cs.mode = 1; cs.mask1 = H2; cs.mask2 = H1;                           // :154, :161
     cs.o1 = G2; cs.o2 = G1;
     cs.P = c.ar->f32((size_t)M * n3pad);

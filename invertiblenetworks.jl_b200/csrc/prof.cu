@@ -1,6 +1,7 @@
 // prof.cu - launch counter and optional CUDA-event profiling of the op families.
 #include "../../include/inb200.h"
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -79,6 +80,10 @@ extern "C" {
 
 long long inb_launch_count(void) { return g_launches.load(); }
 
+int inb_debug_chain_trace(void* dev_buf) {
+  inb::chain_set_trace((long long*)dev_buf);
+  return 0;
+}
 int inb_prof_enable(int on) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!on) collect_locked();
