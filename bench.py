@@ -271,6 +271,15 @@ def main():
         L_.inb_prof_enable(0)
         prof = inb200.lib.prof_table()
 
+    # host-side cost of enqueuing one step (no synchronisation inside): when it approaches the device time the
+    # per-step synchronisation of the end-to-end loop exposes it
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_device()
+    host_enqueue_ms = (time.perf_counter() - t0) * 1e3 / steps
+    barrier()
+
     step_e2e()
     ms_e2e = timed(step_e2e, steps)
     f_last = step_e2e()
@@ -313,7 +322,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": X_host.numel() * 4 * world,
                 "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / steps, "loss": f_last},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roof,
         "model_flops": {"rb_forward_gflop_per_sample": F / 1e9, "fwd_bwd_gflop_per_sample": 4 * F / 1e9,
                         "useful_tflops": 4 * F * value / 1e12, "frac_of_tensor_peak": 4 * F * value / 1e12 / pk["tensor"],

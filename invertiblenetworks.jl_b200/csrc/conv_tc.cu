@@ -170,50 +170,76 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
 
 // im2col of a (B,C,px) fp32 tensor [two sources, conditional cat] into pixel-major bf16 hi/lo rows
 //   col[m][tap*C + c] = x[c][pix(m) + off(tap)]   (zero outside the image = the conv's zero padding),
-// K padded with zeros to kp (multiple of 64) except column `ones_col` (>= 0), which is 1.0: the bias gradient
-// then falls out of the weight-gradient MMA as one more column.  thread = (pixel, group of 8 columns)
-__global__ void k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
-                            long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M,
-                            int kp, int ones_col, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const int groups = kp / 8;
-  const long long total = M * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int gidx = (int)(i % groups);
-    const long long m = i / groups;
-    const long long b = m / px, pix = m - b * px;
-    long long t = pix;
-    const int x = (int)(t % W); t /= W;
-    const int y = (int)(t % H); t /= H;
-    const int z = (int)t;
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat16 hh[2], ll[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k = gidx * 8 + 2 * j + u;
-        float v = 0.f;
-        if (k < T * C) {
-          const int tap = k / C, ch = k - tap * C;
-          int dx = 0, dy = 0, dz = 0;
-          if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
-          const int xx = x + dx, yy = y + dy, zz = z + dz;
-          if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) {
-            const long long q = ((long long)zz * H + yy) * W + xx;
-            v = (ch < c0) ? __ldg(in0 + b * in0_bs + (long long)ch * px + q)
-                          : __ldg(in1 + b * in1_bs + (long long)(ch - c0) * px + q);
-          }
-        } else if (k == ones_col) {
-          v = 1.f;
-        }
-        split_bf16(v, hh[u], ll[u]);
+// K padded with zeros to kp (multiple of 64) except column `ones_col` (>= 0), which is 1.0.
+// thread = pixel.  Phase A walks the (tap, channel) columns of a 64-column chunk with running counters: the
+// loads of a warp are 32 consecutive pixels of one channel plane (coalesced; the 3x3 neighbours re-read L1) and
+// land in a [64 k][32 pixels] fp32 tile in shared memory.  Phase B reads the tile back row by row, splits
+// hi/lo and stores full 128-byte row segments of both planes.
+constexpr int kI2cThreads = 128;
+__global__ void __launch_bounds__(kI2cThreads)
+k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
+            long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M, int kp,
+            int ones_col, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float stg_all[kI2cThreads / 32][64 * 33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* stg = stg_all[wid];
+  const long long m_warp = (long long)blockIdx.x * kI2cThreads + wid * 32;
+  if (m_warp >= M) return;
+  const long long m = m_warp + lane;
+  const bool live = m < M;
+  const long long mc = live ? m : (M - 1);
+  const long long b = mc / px, pix = mc - b * px;
+  long long t = pix;
+  const int x = (int)(t % W); t /= W;
+  const int y = (int)(t % H); t /= H;
+  const int z = (int)t;
+  const float* p0 = in0 + b * in0_bs + pix;
+  const float* p1 = in1 ? in1 + b * in1_bs + pix - (long long)c0 * px : nullptr;
+  int tap = 0, ch = 0;      // running (tap, channel) of column k
+  bool ok = false;          // this pixel's neighbour for `tap` is inside the image
+  long long off = 0;
+  auto set_tap = [&]() {
+    int dx = 0, dy = 0, dz = 0;
+    if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
+    const int xx = x + dx, yy = y + dy, zz = z + dz;
+    ok = live && tap < T && xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
+    off = dx + (long long)dy * W + (long long)dz * W * H;
+  };
+  set_tap();
+  for (int kc = 0; kc < kp; kc += 64) {
+#pragma unroll 4
+    for (int j = 0; j < 64; ++j) {
+      const int k = kc + j;
+      float v = 0.f;
+      if (tap < T) {
+        if (ok) v = (ch < c0) ? __ldg(p0 + (long long)ch * px + off) : __ldg(p1 + (long long)ch * px + off);
+        if (++ch == C) { ch = 0; ++tap; set_tap(); }
+      } else if (k == ones_col) {
+        v = 1.f;
       }
-      h[j] = pack2(hh[0], hh[1]);
-      l[j] = pack2(ll[0], ll[1]);
+      stg[j * 33 + lane] = v;
     }
-    *reinterpret_cast<uint4*>(hi + m * kp + gidx * 8) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + m * kp + gidx * 8) = make_uint4(l[0], l[1], l[2], l[3]);
+    __syncwarp();
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3), k0 = (lane & 7) * 8;
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = stg[(k0 + 2 * q) * 33 + row], bb = stg[(k0 + 2 * q + 1) * 33 + row];
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
+        wh[q] = hw;
+        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
+      }
+      if (m_warp + row < M) {
+        const long long o = (m_warp + row) * kp + kc + k0;
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        *reinterpret_cast<uint4*>(lo + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+    }
+    __syncwarp();
   }
 }
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
@@ -222,8 +248,7 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   const long long M = g.px * B;
   const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
-  const long long total = M * (kp / 8);
-  k_im2col_tc<<<(unsigned)std::min<long long>(cdiv(total, 256), 148 * 32), 256, 0, c.st>>>(
+  k_im2col_tc<<<(unsigned)cdiv(M, kI2cThreads), kI2cThreads, 0, c.st>>>(
       in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M, kp, ones_col, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
 }

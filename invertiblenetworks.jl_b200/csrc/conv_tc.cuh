@@ -76,6 +76,19 @@ struct WgradTcSpec {
 };
 void op_wgrad_tc(Ctx& c, const WgradTcSpec& s);
 
+// Weight / bias gradients of the fused path (conv_tc_wgrad2.cu): dw[p][c][T-1-tap] = sum_pix P[pix][p] Q[pix][tap*C+c],
+// db[p] = sum_pix P[pix][p] (nullable).  P [M][np], Q [M][pitch >= T*C, multiple of 64].
+struct Wgrad2TcSpec {
+  long long M;
+  Planes P;
+  int np;
+  Planes Q;
+  int C, T;
+  float* dw;
+  float* db;
+};
+void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
+
 // Fused pass of the block's three contractions (conv_tc_chain.cu): im2col-GEMM -> per-pixel GEMM ->
 // tap-expanded GEMM + col2im.  mode 0 = forward (bias + ReLU epilogues), mode 1 = backward (relu-grad masks).
 struct ChainSpec {

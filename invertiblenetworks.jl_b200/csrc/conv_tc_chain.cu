@@ -446,32 +446,45 @@ struct Col2imArgs {
 };
 constexpr int kC2iPix = 64;
 
+template <int V>
 __global__ void __launch_bounds__(256) k_col2im(const Col2imArgs a) {
   extern __shared__ float c2i_s[];  // [Cn][kC2iPix + 1]
   const long long m0 = (long long)blockIdx.x * kC2iPix;
-  const int tot = kC2iPix * a.Cn;
-  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-    const int p = i / a.Cn, n = i - p * a.Cn;
+  const int ng = a.Cn / V;  // V consecutive channels per item: lanes walk the channels of a P row first
+  for (int i = threadIdx.x; i < kC2iPix * ng; i += blockDim.x) {
+    const int p = i / ng, g = i - p * ng;
     const long long m = m0 + p;
-    float acc = 0.f;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
     if (m < a.M) {
       long long t = m;
       const int x = (int)(t % a.W); t /= a.W;
       const int y = (int)(t % a.H); t /= a.H;
       const int z = (int)(t % a.D);
+      const float* base = a.P + m * a.n3pad + g * V;
       for (int tap = 0; tap < a.taps; ++tap) {
         int dx, dy, dz;
         chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
         const int xx = x + dx, yy = y + dy, zz = z + dz;
         if (xx < 0 || xx >= a.W || yy < 0 || yy >= a.H || zz < 0 || zz >= a.D) continue;
-        const long long mm = m + dx + (long long)dy * a.W + (long long)dz * a.W * a.H;
-        acc += __ldg(a.P + mm * a.n3pad + tap * a.Cn + n);
+        const float* src = base + (dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.Cn;
+        if (V == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+          acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+        } else if (V == 2) {
+          const float2 q = __ldg(reinterpret_cast<const float2*>(src));
+          acc[0] += q.x; acc[1] += q.y;
+        } else {
+          acc[0] += __ldg(src);
+        }
       }
     }
-    c2i_s[n * (kC2iPix + 1) + p] = acc;
+#pragma unroll
+    for (int v = 0; v < V; ++v) c2i_s[(g * V + v) * (kC2iPix + 1) + p] = acc[v];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kC2iPix * a.Cn; i += blockDim.x) {
     const int n = i / kC2iPix, p = i - n * kC2iPix;
     const long long m = m0 + p;
     if (m >= a.M) continue;
@@ -605,7 +618,10 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     ca.add = s.add; ca.add_bs = s.add_bs; ca.add_n = s.add_n;
     Prof pf(c, F_COL2IM, 1, 0, (4.0 * a.n3pad + 4.0 * s.Cn) * a.M);
     const size_t sm = (size_t)s.Cn * (kC2iPix + 1) * sizeof(float);
-    k_col2im<<<(unsigned)cdiv(a.M, kC2iPix), 256, sm, c.st>>>(ca);
+    const unsigned nb = (unsigned)cdiv(a.M, kC2iPix);
+    if (s.Cn % 4 == 0) k_col2im<4><<<nb, 256, sm, c.st>>>(ca);
+    else if (s.Cn % 2 == 0) k_col2im<2><<<nb, 256, sm, c.st>>>(ca);
+    else k_col2im<1><<<nb, 256, sm, c.st>>>(ca);
     INB_CUDA(cudaGetLastError());
   }
 }

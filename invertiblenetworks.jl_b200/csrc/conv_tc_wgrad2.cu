@@ -1,0 +1,235 @@
+// conv_tc_wgrad2.cu - weight (and bias) gradients of the fused ResidualBlock path on tcgen05.
+//
+//   D[p][q] = sum_{pixels} P[pix][p] * Q[pix][q]          (\nabla conv_filter, layer_residual_block.jl:152,156,163)
+//
+// P = a 128/256-channel hidden gradient or activation [M][np], Q = im2col rows [M][taps*C -> 64k] (3x3 convs: the
+// taps are columns, so there is no tap loop and every TMA row is 128 bytes) or the other hidden tensor (1x1 conv).
+// Both operands are MN-major for the MMA (the contraction index is the pixel = the strided dimension): a TMA box of
+// (64 channels x 32 pixels) lands in shared memory as the canonical MN-major SWIZZLE_128B atom.
+// One persistent CTA per SM owns a contiguous pixel range and ALL np rows (np/128 accumulators of N <= 256 columns
+// in TMEM, so P and Q are read from HBM exactly once); partial sums are added with red.global.add.f32 straight into
+// the reference's weight layout dw[p][c][T-1-tap] (the kernel flip of NNlib's conv).
+// The four epilogue warps are idle during the main loop: they sum the columns of the P tile while it sits in shared
+// memory, which yields the bias gradient db[p] = sum_pix P[pix][p] (:157,164) without another pass over HBM.
+//
+// Warps: 0 TMA producer | 1 MMA issuer | 2..5 bias sums during the loop, TMEM -> dw afterwards.
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+#include "tc_maps.cuh"
+
+#include <algorithm>
+
+namespace inb {
+using namespace tc;
+
+constexpr int kWgPB = 32;  // pixels per k-block
+
+struct Wgrad2Args {
+  long long M;
+  int nblocks, blocks_per_cta;
+  int np, halves;   // rows of D (channels of P), np / 128
+  int nq, ng;       // columns handled by this launch's groups: group g = columns [g*256, ...) of width <= 256
+  int qtot;         // total columns of Q
+  int C, T;         // column q = tap*C + c for q < T*C, other columns are dropped
+  int stages;
+  uint32_t stage_bytes, p_plane, q_plane;  // per plane: P tile, Q tile (of the widest group)
+  float* dw;
+  float* db;        // nullable
+};
+
+template <int NT>
+__global__ void __launch_bounds__(192, 1)
+k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUtensorMap mP1,
+            const __grid_constant__ CUtensorMap mQ0, const __grid_constant__ CUtensorMap mQ1, const Wgrad2Args a) {
+  constexpr int NP = (NT == 1) ? 1 : 2;
+  constexpr uint32_t ATOM = kWgPB * 128;  // 64 channels x 32 pixels
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_bytes);
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = empty + 8;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.y;
+  const int q0 = grp * 256;
+  const int nqg = min(256, a.qtot - q0);  // columns of this group (multiple of 64)
+  const int qatoms = nqg / 64, patoms = a.np / 64;
+  const bool do_bias = a.db != nullptr && grp == 0;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&mP0);
+    prefetch_tmap(&mQ0);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, do_bias ? 1 + patoms : 1); }
+      mbar_init(tfull, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tslot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const int blk0 = blockIdx.x * a.blocks_per_cta;
+  const int nkb = max(min(blk0 + a.blocks_per_cta, a.nblocks) - blk0, 0);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx = NP * (patoms + qatoms) * ATOM;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(empty + s, ((kb / a.stages) & 1) ^ 1);
+        mbar_expect_tx(full + s, tx);
+        const int row0 = (blk0 + kb) * kWgPB;
+        uint8_t* sp = smem + (size_t)s * a.stage_bytes;
+        uint8_t* sq = sp + NP * a.p_plane;
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+          for (int at = 0; at < patoms; ++at)
+            tma_load_2d(pl ? &mP1 : &mP0, full + s, sp + pl * a.p_plane + at * ATOM, at * 64, row0);
+          for (int at = 0; at < qatoms; ++at)
+            tma_load_2d(pl ? &mQ1 : &mQ0, full + s, sq + pl * a.q_plane + at * ATOM, q0 + at * 64, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, nqg, 1, 1);
+      // MN-major SWIZZLE_128B: LBO = byte distance between 64-element atoms along M / N, SBO = 8 pixel rows
+      const uint32_t dhi = (uint32_t)(make_smem_desc(0, ATOM, 1024, LAYOUT_SW128) >> 32);
+      const uint32_t dlo_lbo = ((ATOM >> 4) & 0x3FFF) << 16;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(full + s, (kb / a.stages) & 1);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + (size_t)s * a.stage_bytes);
+        const uint32_t sq = sp + NP * a.p_plane;
+        for (int h = 0; h < a.halves; ++h) {
+#pragma unroll
+          for (int term = 0; term < NT; ++term) {
+            const uint32_t tp = sp + ((term == 2) ? a.p_plane : 0) + h * 2 * ATOM;
+            const uint32_t tq = sq + ((term == 1) ? a.q_plane : 0);
+#pragma unroll
+            for (int k = 0; k < kWgPB / 16; ++k) {
+              const uint64_t ad = ((uint64_t)dhi << 32) | dlo_lbo | (((tp + k * 16 * 128) >> 4) & 0x3FFF);
+              const uint64_t bd = ((uint64_t)dhi << 32) | dlo_lbo | (((tq + k * 16 * 128) >> 4) & 0x3FFF);
+              umma_f16(tmem + h * 256, ad, bd, idesc, (kb > 0 || term > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int ew = warp - 2;  // 0..3
+    if (do_bias && ew < patoms) {
+      // column sums of the P tile (atom ew = channels [64 ew, 64 ew + 64)): lane owns channels 2*lane, 2*lane+1
+      float s0 = 0.f, s1 = 0.f;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(full + s, (kb / a.stages) & 1);
+        const uint8_t* at = smem + (size_t)s * a.stage_bytes + ew * ATOM;
+#pragma unroll 8
+        for (int px = 0; px < kWgPB; ++px) {
+          const uint32_t off = px * 128 + ((((uint32_t)lane >> 2) ^ (px & 7)) << 4) + (lane & 3) * 4;
+          const uint32_t h = *reinterpret_cast<const uint32_t*>(at + off);
+          s0 += bf16lo_to_f(h);
+          s1 += bf16hi_to_f(h);
+          if (NT == 3) {
+            const uint32_t l = *reinterpret_cast<const uint32_t*>(at + a.p_plane + off);
+            s0 += bf16lo_to_f(l);
+            s1 += bf16hi_to_f(l);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+      }
+      if (nkb > 0) {
+        atomicAdd(a.db + ew * 64 + 2 * lane, s0);
+        atomicAdd(a.db + ew * 64 + 2 * lane + 1, s1);
+      }
+    }
+    if (nkb > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int q = warp & 3;  // TMEM lane quadrant
+      const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+      for (int h = 0; h < a.halves; ++h) {
+        const int p = h * 128 + q * 32 + lane;
+        float* dwp = a.dw + (long long)p * a.C * a.T;
+        for (int c0 = 0; c0 < nqg; c0 += 32) {
+          if (q0 + c0 >= a.T * a.C) break;  // only padding columns from here on
+          uint32_t r[32];
+          tmem_ld32(tmem + h * 256 + c0 + lane_sel, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = q0 + c0 + j;
+            if (col < a.T * a.C) {
+              const int tap = col / a.C, cc = col - tap * a.C;
+              atomicAdd(dwp + (long long)cc * a.T + (a.T - 1 - tap), __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
+  INB_CHECK(s.np == 128 || s.np == 256, "tensor-core wgrad: np = %d must be 128 or 256", s.np);
+  INB_CHECK(s.Q.pitch % 64 == 0 && s.P.pitch == s.np, "tensor-core wgrad: operand pitches must be multiples of 64");
+  INB_CHECK(s.T * s.C <= s.Q.pitch, "tensor-core wgrad: Q has %d columns, need %d", s.Q.pitch, s.T * s.C);
+  if (c.dry()) return;
+  const int NT = (c.prec == 1) ? 3 : 1;
+  const int NP = NT == 1 ? 1 : 2;
+  Wgrad2Args a{};
+  a.M = s.M;
+  a.nblocks = (int)cdiv(s.M, kWgPB);
+  a.np = s.np;
+  a.halves = s.np / 128;
+  a.qtot = s.Q.pitch;
+  a.C = s.C;
+  a.T = s.T;
+  a.dw = s.dw;
+  a.db = s.db;
+  const int ng = (int)cdiv(a.qtot, 256);
+  const int nqmax = std::min(a.qtot, 256);
+  a.p_plane = (uint32_t)s.np * kWgPB * 2;
+  a.q_plane = (uint32_t)nqmax * kWgPB * 2;
+  a.stage_bytes = NP * (a.p_plane + a.q_plane);
+  int stages = (int)((225 * 1024) / a.stage_bytes);
+  if (stages > 8) stages = 8;
+  INB_CHECK(stages >= 2, "tensor-core wgrad: stage of %u bytes does not fit", a.stage_bytes);
+  a.stages = stages;
+  const int ctas = std::max(1, 148 / ng);
+  a.blocks_per_cta = (int)cdiv(a.nblocks, ctas);
+  const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);
+  const size_t smem = (size_t)stages * a.stage_bytes + 17 * 8 + 16;
+  CUtensorMap mP0 = make_rows_map(s.P.hi, s.P.pitch, s.M, 64, kWgPB);
+  CUtensorMap mP1 = make_rows_map(s.P.lo, s.P.pitch, s.M, 64, kWgPB);
+  CUtensorMap mQ0 = make_rows_map(s.Q.hi, s.Q.pitch, s.M, 64, kWgPB);
+  CUtensorMap mQ1 = make_rows_map(s.Q.lo, s.Q.pitch, s.M, 64, kWgPB);
+  Prof pf(c, F_WGRAD_TC, 2 + (s.db ? 1 : 0), 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
+  INB_CUDA(cudaMemsetAsync(s.dw, 0, (size_t)s.np * s.C * s.T * sizeof(float), c.st));
+  if (s.db) INB_CUDA(cudaMemsetAsync(s.db, 0, (size_t)s.np * sizeof(float), c.st));
+  dim3 grid(gx, ng, 1);
+  if (NT == 3) {
+    INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad2_tc<3><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, a);
+  } else {
+    INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, a);
+  }
+  INB_CUDA(cudaGetLastError());
+}
+
+}  // namespace inb

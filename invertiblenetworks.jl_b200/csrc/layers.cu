@@ -157,6 +157,11 @@ static Planes planes_at(void* mem, long long M, int pitch) {
 static Planes planes_new(Ctx& c, long long rows, int pitch) {
   return planes_at(c.ar->alloc_bytes((size_t)rows * pitch * 2 * 2), rows, pitch);
 }
+// the fused chain runs both directions of the block or neither (the hidden tensors change layout owner)
+static bool rb_chain_ok(const RBShape& s) {
+  return chain_supported(s.g, s.B, s.k1, s.k2, s.nh, s.Cin(), s.Cout) &&
+         chain_supported(s.g, s.B, s.k1, s.k2, s.nh, s.Cout, s.Cin());
+}
 static ConvTcSpec tc_base(const RBShape& s) {
   ConvTcSpec cs{};
   cs.g = s.g;
@@ -170,25 +175,23 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   const long long px = s.g.px, M = px * s.B;
   const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2();
   const int cin_pad = pad16(Cin), cout_pad = pad16(s.Cout);
-  // the padded bf16 copy of the block input outlives this call (wgrad1 reads it again)
-  h.xin = planes_new(c, M, cin_pad);
-  op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
-  size_t m = c.ar->mark();
-  Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
-  if (chain_supported(s.g, s.B, s.k1, s.k2, nh, Cin, s.Cout)) {
+  if (rb_chain_ok(s)) {
     // one fused kernel for the three contractions (conv_tc_chain.cu); the hidden tensors reach HBM only
-    // when a backward pass follows (h.G != nullptr: the recompute of flow_backward)
+    // when a backward pass follows (h.G != nullptr: the recompute of flow_backward).  The im2col rows of the
+    // block input outlive this call: the weight gradient of conv1 reads them again.
+    const int kp = chain_kpad(T1, Cin, 0);
+    h.xin = planes_new(c, M, kp);
+    op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, -1, h.xin);
+    size_t m = c.ar->mark();
+    Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
     const int n3pad = chain_n3pad(T1, s.Cout);
-    const int kp = chain_kpad(T1, Cin, 1);
     Planes W1 = planes_new(c, nh, kp), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
-    Planes xcol = planes_new(c, M, kp);
-    op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, T1 * Cin, xcol);
     op_pack_w_dense_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, kp, W1);
     op_pack_w_tc(c, PACK_CONV, nh, nh, 1, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
     op_pack_wexp_tc(c, nh, s.Cout, T1, p.W3, n3pad, W3);
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
-    cs.in = xcol; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
+    cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
     cs.mode = 0; cs.bias1 = p.b1; cs.bias2 = p.b2;
     if (h.G) { cs.o1 = H1; cs.o2 = H2; }
     cs.P = c.ar->f32((size_t)M * n3pad);
@@ -198,6 +201,11 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     c.ar->release(m);
     return;
   }
+  // the padded bf16 copy of the block input outlives this call (wgrad1 reads it again)
+  h.xin = planes_new(c, M, cin_pad);
+  op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
+  size_t m = c.ar->mark();
+  Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
   Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, T2 * nh), W3 = planes_new(c, cout_pad, T1 * nh);
   op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
   op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
@@ -232,16 +240,12 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
   const int cin_pad = pad16(Cin), cout_pad = pad16(Cout);
   size_t m = c.ar->mark();
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh), G2 = planes_at(h.G, M, nh);
-  Planes G1 = H2;  // dY1 reuses X3's storage once dW3 and the dgrad3 mask have consumed it
-  Planes dY3p = planes_new(c, M, cout_pad);
-  op_nchw_to_tc(c, s.g, s.B, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, cout_pad, dY3p);
-  const bool chain = chain_supported(s.g, s.B, s.k1, s.k2, nh, Cout, Cin);
-  if (chain) {
-    // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the
-    // weight gradients below, so dY1 needs its own buffer here
-    G1 = planes_new(c, M, nh);
-    const int n3pad = chain_n3pad(T1, Cin);
+  if (rb_chain_ok(s)) {
+    // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the weight
+    // gradients, which read every hidden tensor exactly once and produce the bias gradients on the way
+    Planes G1 = planes_new(c, M, nh);
     const int kp = chain_kpad(T1, Cout, 0);
+    const int n3pad = chain_n3pad(T1, Cin);
     Planes W3c = planes_new(c, nh, kp), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
     Planes dcol = planes_new(c, M, kp);
     op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol);
@@ -258,11 +262,19 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
     cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
     op_rb_chain(c, cs);
+    op_wgrad2_tc(c, Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr});   // :152
+    op_wgrad2_tc(c, Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2});           // :156-157
+    op_wgrad2_tc(c, Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1});      // :163-164
+    c.ar->release(m);
+    return;
   }
+  Planes G1 = H2;  // dY1 reuses X3's storage once dW3 and the dgrad3 mask have consumed it
+  Planes dY3p = planes_new(c, M, cout_pad);
+  op_nchw_to_tc(c, s.g, s.B, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, cout_pad, dY3p);
   const int kmax = std::max(T1 * std::max(cout_pad, nh), T2 * nh);
   Planes Wp = planes_new(c, std::max(nh, cin_pad), kmax);
   auto wview = [&](int rows, int k) { return planes_at(Wp.hi, rows, k); };
-  if (!chain) {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
+  {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
     Planes W = wview(nh, T1 * cout_pad);
     op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W);
     ConvTcSpec cs = tc_base(s);
@@ -276,7 +288,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     ws.dw = gr.W3;
     op_wgrad_tc(c, ws);
   }
-  if (!chain) {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
+  {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
     Planes W = wview(nh, T2 * nh);
     op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W, 1);  // + I: the '+ dY2' of :155
     ConvTcSpec cs = tc_base(s);
@@ -291,7 +303,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     op_wgrad_tc(c, ws);
     op_colsum_tc(c, M, nh, G2, gr.b2);
   }
-  if (!chain) {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
+  {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
     Planes W = wview(cin_pad, T1 * nh);
     op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, W);
     ConvTcSpec cs = tc_base(s);
