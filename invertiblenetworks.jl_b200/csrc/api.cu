@@ -7,6 +7,8 @@
 #include <memory>
 #include <algorithm>
 #include <stdexcept>
+#include <initializer_list>
+#include <cstdlib>
 
 namespace inb {
 
@@ -90,6 +92,14 @@ struct inb_plan {
   size_t persist = 0;  // bytes at the start of the arena that survive calls (logdet accumulator)
   size_t need = 0;     // workspace bytes (sizing pass at plan creation)
   double* ld = nullptr;
+  // CUDA graphs of the network-level calls (slot 0 forward, 1 inverse, 2 backward): a call with the same
+  // pointers and batch as the captured one replays ~1500 launches with a single cudaGraphLaunch
+  struct GraphSlot {
+    uint64_t key = 0;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+  } graphs[3];
+  cudaStream_t capture_stream = nullptr;
 };
 
 static int an_index(const inb_plan* p, int i, int j, int which) { return 2 * (i * p->d.K + j) + which; }
@@ -383,6 +393,96 @@ static void check_desc(const inb_glow_desc* d) {
   INB_CHECK(d->sig_high > d->sig_low, "sigmoid high must exceed low");
 }
 
+static void check_call(inb_plan* p, int batch, bool want_cond) {
+  INB_CHECK(p != nullptr, "null plan");
+  INB_CHECK(p->cond == want_cond, want_cond ? "plan is not conditional (n_cond == 0)"
+                                            : "plan is conditional: use the inb_cglow_* entry points");
+  INB_CHECK(batch >= 1 && batch <= p->d.batch, "batch %d outside the plan's range [1, %d]", batch, p->d.batch);
+}
+static Ctx call_ctx(inb_plan* p, void* stream) {
+  if (!p->ar.base) {
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, p->need);
+    if (e != cudaSuccess) fail(INB_ERR_NOMEM, "workspace of %zu bytes: %s", p->need, cudaGetErrorString(e));
+    p->ar.base = (char*)base;
+    p->ar.cap = p->need;
+    p->ar.dry = false;
+    p->ar.off = 0;
+    p->ld = (double*)p->ar.alloc_bytes(256);
+    p->persist = p->ar.off;
+  }
+  p->ar.off = p->persist;
+  return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
+}
+
+// ---------------------------------------------------------------- CUDA-graph replay of whole-network calls
+static uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+  return h;
+}
+static uint64_t key_of(const inb_plan* p, int batch, std::initializer_list<const void*> ptrs, float* const* params,
+                       float* const* grads) {
+  uint64_t h = mix(0x1234567ull, (uint64_t)batch);
+  for (const void* q : ptrs) h = mix(h, (uint64_t)(uintptr_t)q);
+  const int n = 10 * p->d.L * p->d.K + (p->cond ? 2 : 0);
+  for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)params[i]);
+  if (grads)
+    for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)grads[i]);
+  return h | 1ull;
+}
+static bool graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("INB_GRAPHS");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+// `enqueue(ctx)` launches the call's kernels on ctx.st.  First call with a given key: capture on the plan's
+// private stream (nothing executes during capture), instantiate, launch on the caller's stream; later calls
+// with the same key: one cudaGraphLaunch.  Falls back to direct launches while profiling, inside a caller's own
+// capture, or with INB_GRAPHS=0.
+template <class F>
+static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& enqueue) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+  cudaGetLastError();
+  if (!graphs_enabled() || capturing || prof_is_enabled()) {
+    Ctx c = call_ctx(p, stream);
+    enqueue(c);
+    return;
+  }
+  inb_plan::GraphSlot& g = p->graphs[slot];
+  if (g.exec == nullptr || g.key != key) {
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (!p->capture_stream) INB_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+    Ctx c = call_ctx(p, p->capture_stream);
+    const long long n0 = launch_count_now();
+    INB_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
+    cudaGraph_t graph = nullptr;
+    try {
+      enqueue(c);
+    } catch (...) {
+      cudaStreamEndCapture(p->capture_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      throw;
+    }
+    INB_CUDA(cudaStreamEndCapture(p->capture_stream, &graph));
+    g.launches = launch_count_now() - n0;
+    launch_count_add(-g.launches);  // counted again at every replay below
+    cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      g.exec = nullptr;
+      fail(2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    g.key = key;
+  }
+  INB_CUDA(cudaGraphLaunch(g.exec, st));
+  launch_count_add(g.launches);
+}
+
 extern "C" {
 
 const char* inb_last_error(void) { return g_last_error.c_str(); }
@@ -428,6 +528,9 @@ int inb_glow_plan_create(const inb_glow_desc* desc, inb_plan** out) {
 int inb_glow_plan_destroy(inb_plan* p) {
   return guarded([&] {
     if (!p) return;
+    for (auto& g : p->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;
   });
@@ -483,43 +586,27 @@ int inb_glow_zdims(const inb_plan* p, int batch, int scale, int* dims5) {
   return n;
 }
 
-static void check_call(inb_plan* p, int batch, bool want_cond) {
-  INB_CHECK(p != nullptr, "null plan");
-  INB_CHECK(p->cond == want_cond, want_cond ? "plan is not conditional (n_cond == 0)"
-                                            : "plan is conditional: use the inb_cglow_* entry points");
-  INB_CHECK(batch >= 1 && batch <= p->d.batch, "batch %d outside the plan's range [1, %d]", batch, p->d.batch);
-}
-static Ctx call_ctx(inb_plan* p, void* stream) {
-  if (!p->ar.base) {
-    void* base = nullptr;
-    cudaError_t e = cudaMalloc(&base, p->need);
-    if (e != cudaSuccess) fail(INB_ERR_NOMEM, "workspace of %zu bytes: %s", p->need, cudaGetErrorString(e));
-    p->ar.base = (char*)base;
-    p->ar.cap = p->need;
-    p->ar.dry = false;
-    p->ar.off = 0;
-    p->ld = (double*)p->ar.alloc_bytes(256);
-    p->persist = p->ar.off;
-  }
-  p->ar.off = p->persist;
-  return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
-}
-
 int inb_glow_forward(inb_plan* p, int batch, const float* X, float* const* params, float* Z, float* logdet,
                      int init_actnorm, void* stream) {
   return guarded([&] {
     check_call(p, batch, false);
     INB_CHECK(X && params && Z, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_forward(p, c, batch, X, nullptr, params, Z, nullptr, logdet, init_actnorm);
+    if (init_actnorm) {  // data-dependent initialisation: never replayed
+      Ctx c = call_ctx(p, stream);
+      drive_forward(p, c, batch, X, nullptr, params, Z, nullptr, logdet, init_actnorm);
+      return;
+    }
+    run_graphed(p, 0, key_of(p, batch, {X, Z, logdet}, params, nullptr), stream,
+                [&](Ctx& c) { drive_forward(p, c, batch, X, nullptr, params, Z, nullptr, logdet, 0); });
   });
 }
 int inb_glow_inverse(inb_plan* p, int batch, const float* Z, float* const* params, float* X, void* stream) {
   return guarded([&] {
     check_call(p, batch, false);
     INB_CHECK(X && params && Z, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_reverse(p, c, batch, false, nullptr, Z, nullptr, params, nullptr, nullptr, X, nullptr);
+    run_graphed(p, 1, key_of(p, batch, {Z, X}, params, nullptr), stream, [&](Ctx& c) {
+      drive_reverse(p, c, batch, false, nullptr, Z, nullptr, params, nullptr, nullptr, X, nullptr);
+    });
   });
 }
 int inb_glow_backward(inb_plan* p, int batch, const float* dZ, const float* Z, float* const* params,
@@ -527,8 +614,9 @@ int inb_glow_backward(inb_plan* p, int batch, const float* dZ, const float* Z, f
   return guarded([&] {
     check_call(p, batch, false);
     INB_CHECK(dZ && Z && params && grads && dX && X, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_reverse(p, c, batch, true, dZ, Z, nullptr, params, grads, dX, X, nullptr);
+    run_graphed(p, 2, key_of(p, batch, {dZ, Z, dX, X}, params, grads), stream, [&](Ctx& c) {
+      drive_reverse(p, c, batch, true, dZ, Z, nullptr, params, grads, dX, X, nullptr);
+    });
   });
 }
 int inb_cglow_forward(inb_plan* p, int batch, const float* X, const float* C, float* const* params,
@@ -536,8 +624,13 @@ int inb_cglow_forward(inb_plan* p, int batch, const float* X, const float* C, fl
   return guarded([&] {
     check_call(p, batch, true);
     INB_CHECK(X && C && params && ZX && ZC, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_forward(p, c, batch, X, C, params, ZX, ZC, logdet, init_actnorm);
+    if (init_actnorm) {
+      Ctx c = call_ctx(p, stream);
+      drive_forward(p, c, batch, X, C, params, ZX, ZC, logdet, init_actnorm);
+      return;
+    }
+    run_graphed(p, 0, key_of(p, batch, {X, C, ZX, ZC, logdet}, params, nullptr), stream,
+                [&](Ctx& c) { drive_forward(p, c, batch, X, C, params, ZX, ZC, logdet, 0); });
   });
 }
 int inb_cglow_inverse(inb_plan* p, int batch, const float* ZX, const float* ZC, float* const* params,
@@ -545,8 +638,9 @@ int inb_cglow_inverse(inb_plan* p, int batch, const float* ZX, const float* ZC, 
   return guarded([&] {
     check_call(p, batch, true);
     INB_CHECK(ZX && ZC && params && X, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_reverse(p, c, batch, false, nullptr, ZX, ZC, params, nullptr, nullptr, X, nullptr);
+    run_graphed(p, 1, key_of(p, batch, {ZX, ZC, X}, params, nullptr), stream, [&](Ctx& c) {
+      drive_reverse(p, c, batch, false, nullptr, ZX, ZC, params, nullptr, nullptr, X, nullptr);
+    });
   });
 }
 int inb_cglow_backward(inb_plan* p, int batch, const float* dZX, const float* ZX, const float* ZC,
@@ -555,8 +649,9 @@ int inb_cglow_backward(inb_plan* p, int batch, const float* dZX, const float* ZX
   return guarded([&] {
     check_call(p, batch, true);
     INB_CHECK(dZX && ZX && ZC && params && grads && dX && X && dC, "null tensor argument");
-    Ctx c = call_ctx(p, stream);
-    drive_reverse(p, c, batch, true, dZX, ZX, ZC, params, grads, dX, X, dC);
+    run_graphed(p, 2, key_of(p, batch, {dZX, ZX, ZC, dX, X, dC}, params, grads), stream, [&](Ctx& c) {
+      drive_reverse(p, c, batch, true, dZX, ZX, ZC, params, grads, dX, X, dC);
+    });
   });
 }
 

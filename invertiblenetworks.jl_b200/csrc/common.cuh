@@ -107,6 +107,10 @@ struct Prof {
   ~Prof();
 };
 
+bool prof_is_enabled();
+long long launch_count_now();
+void launch_count_add(long long n);
+
 // Int(round(C/2)) with ties-to-even (dimensionality_operations.jl:408)
 inline int split_k(int C) {
   int h = C / 2;

@@ -197,24 +197,25 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
   const float* p1 = in1 ? in1 + b * in1_bs + pix - (long long)c0 * px : nullptr;
   int tap = 0, ch = 0;      // running (tap, channel) of column k
   bool ok = false;          // this pixel's neighbour for `tap` is inside the image
-  long long off = 0;
+  const float* src = p0;    // running pointer: channel `ch` of that neighbour
   auto set_tap = [&]() {
     int dx = 0, dy = 0, dz = 0;
     if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
     const int xx = x + dx, yy = y + dy, zz = z + dz;
     ok = live && tap < T && xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
-    off = dx + (long long)dy * W + (long long)dz * W * H;
+    src = ((c0 > 0) ? p0 : p1) + (dx + (long long)dy * W + (long long)dz * W * H);
   };
   set_tap();
   for (int kc = 0; kc < kp; kc += 64) {
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < 64; ++j) {
-      const int k = kc + j;
       float v = 0.f;
       if (tap < T) {
-        if (ok) v = (ch < c0) ? __ldg(p0 + (long long)ch * px + off) : __ldg(p1 + (long long)ch * px + off);
+        if (ok) v = __ldg(src);
+        src += px;
         if (++ch == C) { ch = 0; ++tap; set_tap(); }
-      } else if (k == ones_col) {
+        else if (ch == c0) src = p1 + (long long)ch * px + (src - p0 - (long long)ch * px);  // switch to the second source
+      } else if (kc + j == ones_col) {
         v = 1.f;
       }
       stg[j * 33 + lane] = v;

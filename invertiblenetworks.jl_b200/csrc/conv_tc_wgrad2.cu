@@ -7,8 +7,9 @@
 // Both operands are MN-major for the MMA (the contraction index is the pixel = the strided dimension): a TMA box of
 // (64 channels x 32 pixels) lands in shared memory as the canonical MN-major SWIZZLE_128B atom.
 // One persistent CTA per SM owns a contiguous pixel range and ALL np rows (np/128 accumulators of N <= 256 columns
-// in TMEM, so P and Q are read from HBM exactly once); partial sums are added with red.global.add.f32 straight into
-// the reference's weight layout dw[p][c][T-1-tap] (the kernel flip of NNlib's conv).
+// in TMEM, so P and Q are read from HBM exactly once).  Each CTA stores its partial D tile (TMA store through a
+// swizzled staging tile) and k_wgrad_reduce sums the partials in a fixed order straight into the reference's weight
+// layout dw[p][c][T-1-tap] (the kernel flip of NNlib's conv): deterministic, and cheaper than np*nq atomics per CTA.
 // The four epilogue warps are idle during the main loop: they sum the columns of the P tile while it sits in shared
 // memory, which yields the bias gradient db[p] = sum_pix P[pix][p] (:157,164) without another pass over HBM.
 //
@@ -33,14 +34,14 @@ struct Wgrad2Args {
   int C, T;         // column q = tap*C + c for q < T*C, other columns are dropped
   int stages;
   uint32_t stage_bytes, p_plane, q_plane;  // per plane: P tile, Q tile (of the widest group)
-  float* dw;
-  float* db;        // nullable
+  float* dbpart;    // [gridDim.x][np] partial bias sums, nullable
 };
 
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUtensorMap mP1,
-            const __grid_constant__ CUtensorMap mQ0, const __grid_constant__ CUtensorMap mQ1, const Wgrad2Args a) {
+            const __grid_constant__ CUtensorMap mQ0, const __grid_constant__ CUtensorMap mQ1,
+            const __grid_constant__ CUtensorMap mD, const Wgrad2Args a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
   constexpr uint32_t ATOM = kWgPB * 128;  // 64 channels x 32 pixels
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -53,7 +54,7 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   const int q0 = grp * 256;
   const int nqg = min(256, a.qtot - q0);  // columns of this group (multiple of 64)
   const int qatoms = nqg / 64, patoms = a.np / 64;
-  const bool do_bias = a.db != nullptr && grp == 0;
+  const bool do_bias = a.dbpart != nullptr && grp == 0;
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -149,34 +150,41 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
       }
-      if (nkb > 0) {
-        atomicAdd(a.db + ew * 64 + 2 * lane, s0);
-        atomicAdd(a.db + ew * 64 + 2 * lane + 1, s1);
-      }
+      *reinterpret_cast<float2*>(a.dbpart + (long long)blockIdx.x * a.np + ew * 64 + 2 * lane) = make_float2(s0, s1);
     }
-    if (nkb > 0) {
+    {
+      // partial tile -> scratch: the pipeline stages are free now and serve as the staging area of the TMA store
+      // (SWIZZLE_128B boxes of 32 fp32 columns x 128 rows, as for P in the fused chain)
       mbar_wait(tfull, 0);
       tc_fence_after();
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every bias warp has finished reading the last stages
       const int q = warp & 3;  // TMEM lane quadrant
+      const int row = q * 32 + lane;
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+      const int tid = ew * 32 + lane;
       for (int h = 0; h < a.halves; ++h) {
-        const int p = h * 128 + q * 32 + lane;
-        float* dwp = a.dw + (long long)p * a.C * a.T;
+        if (h > 0) {
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         for (int c0 = 0; c0 < nqg; c0 += 32) {
-          if (q0 + c0 >= a.T * a.C) break;  // only padding columns from here on
           uint32_t r[32];
           tmem_ld32(tmem + h * 256 + c0 + lane_sel, r);
           tmem_ld_wait();
+          uint8_t* g = smem + (size_t)(c0 >> 5) * 16384 + row * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = q0 + c0 + j;
-            if (col < a.T * a.C) {
-              const int tap = col / a.C, cc = col - tap * a.C;
-              atomicAdd(dwp + (long long)cc * a.T + (a.T - 1 - tap), __uint_as_float(r[j]));
-            }
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(g + ((j ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+          const int drow = ((grp * (int)gridDim.x + (int)blockIdx.x) * a.np) + h * 128;
+          for (int c0 = 0; c0 < nqg; c0 += 32) tma_store_2d(&mD, smem + (size_t)(c0 >> 5) * 16384, c0, drow);
+          bulk_commit();
         }
       }
+      if (tid == 0) bulk_wait0();
     }
   }
   tc_fence_before();
@@ -184,11 +192,35 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p]; fixed summation order
+__global__ void k_wgrad_reduce(const float* __restrict__ part, int ncta, int np, int pitch, int qtot, int C, int T,
+                               float* __restrict__ dw, const float* __restrict__ dbpart, float* __restrict__ db) {
+  const int ncol = T * C;
+  const long long total = (long long)np * ncol;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + (dbpart ? np : 0);
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i >= total) {
+      const int p = (int)(i - total);
+      float s = 0.f;
+      for (int k = 0; k < ncta; ++k) s += dbpart[(long long)k * np + p];
+      db[p] = s;
+      continue;
+    }
+    const int col = (int)(i % ncol), p = (int)(i / ncol);
+    const int g = col >> 8, cg = col & 255;
+    const float* src = part + ((long long)g * ncta * np + p) * pitch + cg;
+    float s = 0.f;
+    for (int k = 0; k < ncta; ++k) s += src[(long long)k * np * pitch];
+    const int tap = col / C, cc = col - tap * C;
+    dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
+  }
+  (void)qtot;
+}
+
 void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   INB_CHECK(s.np == 128 || s.np == 256, "tensor-core wgrad: np = %d must be 128 or 256", s.np);
   INB_CHECK(s.Q.pitch % 64 == 0 && s.P.pitch == s.np, "tensor-core wgrad: operand pitches must be multiples of 64");
   INB_CHECK(s.T * s.C <= s.Q.pitch, "tensor-core wgrad: Q has %d columns, need %d", s.Q.pitch, s.T * s.C);
-  if (c.dry()) return;
   const int NT = (c.prec == 1) ? 3 : 1;
   const int NP = NT == 1 ? 1 : 2;
   Wgrad2Args a{};
@@ -199,8 +231,6 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   a.qtot = s.Q.pitch;
   a.C = s.C;
   a.T = s.T;
-  a.dw = s.dw;
-  a.db = s.db;
   const int ng = (int)cdiv(a.qtot, 256);
   const int nqmax = std::min(a.qtot, 256);
   a.p_plane = (uint32_t)s.np * kWgPB * 2;
@@ -209,27 +239,38 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   int stages = (int)((225 * 1024) / a.stage_bytes);
   if (stages > 8) stages = 8;
   INB_CHECK(stages >= 2, "tensor-core wgrad: stage of %u bytes does not fit", a.stage_bytes);
+  INB_CHECK((size_t)stages * a.stage_bytes >= (size_t)(nqmax / 32) * 16384, "tensor-core wgrad: staging does not fit");
   a.stages = stages;
   const int ctas = std::max(1, 148 / ng);
   a.blocks_per_cta = (int)cdiv(a.nblocks, ctas);
-  const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);
+  const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);  // every CTA owns at least one block
+  // scratch: partial tiles [ng][gx][np][nqmax] and partial bias sums [gx][np]
+  size_t mk = c.ar->mark();
+  float* part = c.ar->f32((size_t)ng * gx * s.np * nqmax);
+  float* dbpart = c.ar->f32((size_t)gx * s.np);  // sized in the dry run too (gradient pointers are fake there)
+  a.dbpart = s.db ? dbpart : nullptr;
+  if (c.dry()) { c.ar->release(mk); return; }
   const size_t smem = (size_t)stages * a.stage_bytes + 17 * 8 + 16;
   CUtensorMap mP0 = make_rows_map(s.P.hi, s.P.pitch, s.M, 64, kWgPB);
   CUtensorMap mP1 = make_rows_map(s.P.lo, s.P.pitch, s.M, 64, kWgPB);
   CUtensorMap mQ0 = make_rows_map(s.Q.hi, s.Q.pitch, s.M, 64, kWgPB);
   CUtensorMap mQ1 = make_rows_map(s.Q.lo, s.Q.pitch, s.M, 64, kWgPB);
-  Prof pf(c, F_WGRAD_TC, 2 + (s.db ? 1 : 0), 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
-  INB_CUDA(cudaMemsetAsync(s.dw, 0, (size_t)s.np * s.C * s.T * sizeof(float), c.st));
-  if (s.db) INB_CUDA(cudaMemsetAsync(s.db, 0, (size_t)s.np * sizeof(float), c.st));
+  CUtensorMap mD = make_rows_map_f32(part, nqmax, (long long)ng * gx * s.np, 32, 128);
+  Prof pf(c, F_WGRAD_TC, 2, 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
   dim3 grid(gx, ng, 1);
   if (NT == 3) {
     INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad2_tc<3><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, a);
+    k_wgrad2_tc<3><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   } else {
     INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, a);
+    k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   }
   INB_CUDA(cudaGetLastError());
+  const long long outs = (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
+  k_wgrad_reduce<<<(unsigned)std::min<long long>(cdiv(outs, 256), 148 * 8), 256, 0, c.st>>>(
+      part, (int)gx, s.np, nqmax, a.qtot, s.C, s.T, s.dw, a.dbpart, s.db);
+  INB_CUDA(cudaGetLastError());
+  c.ar->release(mk);
 }
 
 }  // namespace inb

@@ -74,6 +74,12 @@ static void collect_locked() {
 
 }  // namespace inb
 
+namespace inb {
+bool prof_is_enabled() { return g_on.load(std::memory_order_relaxed) != 0; }
+long long launch_count_now() { return g_launches.load(); }
+void launch_count_add(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace inb
+
 using namespace inb;
 
 extern "C" {
