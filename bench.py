@@ -209,7 +209,7 @@ def main():
     if rank == 0:
         G.forward(X)
     if world > 1:
-        dist.broadcast(G.flat_params, src=0)
+        inb200.dp.broadcast_params(G.flat_params, src=0)
         G._mark_initialized()
 
     def step_device():
@@ -218,7 +218,7 @@ def main():
         G.backward(dZ, Z)
         inb200.clear_grad(G)
         if world > 1:
-            dist.all_reduce(G.flat_grads, op=dist.ReduceOp.AVG)
+            inb200.dp.allreduce_grads(G.flat_grads)
         return nll, ld
 
     loss_host = torch.empty(2).pin_memory()

@@ -6,6 +6,7 @@ contains a dot).  Compute lives in csrc/ -> libinb200.so (C ABI: include/inb200.
 it with ctypes; glow.py mirrors the reference's Julia API on torch CUDA tensors.
 """
 from . import lib
+from . import dp
 from .lib import InbError, PRECISIONS
 from .glow import (ActNorm, Conv1x1, CouplingLayerGlow, NetworkConditionalGlow, NetworkGlow, NetworkGlow3D,
                    Parameter, ResidualBlock, clear_grad, get_grads, get_params, nll_grad, set_params, squeeze,
@@ -16,5 +17,5 @@ ConditionalLayerGlow = CouplingLayerGlow  # same class with n_cond > 0 (conditio
 __all__ = [
     "ActNorm", "Conv1x1", "CouplingLayerGlow", "ConditionalLayerGlow", "NetworkConditionalGlow", "NetworkGlow",
     "NetworkGlow3D", "Parameter", "ResidualBlock", "clear_grad", "get_grads", "get_params", "nll_grad",
-    "set_params", "squeeze", "unsqueeze", "InbError", "PRECISIONS", "lib",
+    "set_params", "squeeze", "unsqueeze", "InbError", "PRECISIONS", "lib", "dp",
 ]
