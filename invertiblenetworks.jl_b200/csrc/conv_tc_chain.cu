@@ -27,6 +27,7 @@
 #include "tc_maps.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace inb {
 using namespace tc;
@@ -433,6 +434,361 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------- chain with the hidden operand in tensor memory
+// Same pipeline as k_rb_chain, but E1 / E2 write the bf16 hi/lo hidden tile back into TENSOR MEMORY (tcgen05.st, in
+// place of the fp32 accumulator they just read) and GEMM2 / GEMM3 take their A operand from there
+// (tcgen05.mma [d], [a_tmem], b_desc).  k_rb_chain is shared-memory-bandwidth bound: per tile the MMAs read ~1.3 MB of
+// operands next to ~0.5 MB of TMA writes and ~0.4 MB of epilogue traffic against 128 B/clk.  With A in TMEM the
+// MMAs read only the streamed weights, the 128 KB operand buffer disappears and the ring gets deeper.
+// Column map of a 64-channel chunk c of the 256-column region R:  warp half h (channels 32h..32h+31) reads fp32
+// columns R+64c+32h..+31 and overwrites them with 16 packed hi words (R+64c+32h..+15) and 16 packed lo words
+// (+16..+31); k-step kk = 2h + j of the chunk starts at column R+64c+32h+8j (hi) / +16 (lo).
+// Shared memory: [64 KB staging: two 32 KB slots for the TMA stores of the hidden chunks | the P slab of E3]
+//                [ring of NP x 16 KB weight / im2col stages][barriers, biases].
+template <int NT>
+__global__ void __launch_bounds__(kChainThreads, 1)
+k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
+  constexpr int NP = (NT == 1) ? 1 : 2;
+  constexpr uint32_t STAGE = NP * kPlane;
+  constexpr uint32_t SLOT = 2 * kPlane;  // one staging slot: hi + lo planes of a 128 x 64 chunk
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stag = smem;
+  uint8_t* ring = stag + 2 * SLOT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * STAGE);
+  uint64_t* empty = full + 8;
+  uint64_t* dfull = empty + 8;    // [3]
+  uint64_t* hready = dfull + 3;   // [4]  chunk c of the hidden operand is in tensor memory
+  uint64_t* sready = hready + 4;  // [2]  staging slot written (store mode)
+  uint64_t* sfree = sready + 2;   // [2]  staging slot read by its TMA store
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sfree + 3);  // 28 barrier slots (one spare) keep sbias 16-byte aligned
+  float* sbias = reinterpret_cast<float*>(tslot + 4);        // [2][256]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&maps.A[0]);
+    prefetch_tmap(&maps.W1[0]);
+    prefetch_tmap(&maps.W2[0]);
+    prefetch_tmap(&maps.W3[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+      for (int s = 0; s < 3; ++s) mbar_init(dfull + s, 1);
+      for (int s = 0; s < 4; ++s) mbar_init(hready + s, 8);
+      for (int s = 0; s < 2; ++s) { mbar_init(sready + s, 8); mbar_init(sfree + s, 1); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tslot, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const float* bp = (i < 256) ? a.bias1 : a.bias2;
+    const int j = i & 255;
+    sbias[i] = (bp && j < a.nh) ? bp[j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (identical to k_rb_chain)
+    if (elect_one()) {
+      uint32_t it = 0;
+      auto acquire = [&](uint32_t tx) -> uint8_t* {
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, tx);
+        return ring + (size_t)s * STAGE;
+      };
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.A[pl], fb, st + pl * kPlane, kb * 64, tile * 128);
+            ++it;
+          }
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W1[pl], fb, st + pl * kPlane, kb * 64, nhf * 128);
+          }
+        }
+        for (int c = 0; c < a.nchunk; ++c) {
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W2[pl], fb, st + pl * kPlane, c * 64, nhf * 128);
+          }
+        }
+        for (int pc = 0; pc < a.np3; ++pc) {
+          for (int c = 0; c < a.nchunk; ++c, ++it) {
+            uint8_t* st = acquire(NP * kPlane);
+            uint64_t* fb = full + it % a.stages;
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W3[pl], fb, st + pl * kPlane, c * 64, pc * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_2 = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
+      uint32_t it = 0, tl = 0;
+      auto stage_wait = [&]() -> uint32_t {
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        return smem_u32(ring + (size_t)s * STAGE);
+      };
+      // GEMM1: A (im2col block) and B both in shared memory
+      auto mma_block_ss = [&](uint32_t d_tmem, uint32_t idesc, uint32_t a_addr, uint32_t b_addr, uint32_t first) {
+        const uint32_t alo = (a_addr >> 4) & 0x3FFF, blo = (b_addr >> 4) & 0x3FFF;
+#pragma unroll
+        for (int term = 0; term < NT; ++term) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ((uint64_t)dhi << 32) | (alo + ((term == 2) ? (kPlane >> 4) : 0) + 2 * k);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            umma_f16(d_tmem, ad, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
+          }
+        }
+      };
+      // GEMM2 / GEMM3: A = chunk c of the hidden operand in tensor memory (region ra), B = weight block in smem
+      auto mma_block_ts = [&](uint32_t d_tmem, uint32_t idesc, uint32_t ra, int c, uint32_t b_addr, uint32_t first) {
+        const uint32_t blo = (b_addr >> 4) & 0x3FFF;
+#pragma unroll
+        for (int term = 0; term < NT; ++term) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t at = ra + 64 * c + 32 * (k >> 1) + 8 * (k & 1) + ((term == 2) ? 16 : 0);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            umma_f16_ts(d_tmem, at, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
+          }
+        }
+      };
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tl) {
+        const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
+        long long* tr = (a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
+        if (tr) tr[0] = clock64();
+        if (tl > 0) {  // R0 held the A operand of the previous tile's GEMM3: let those MMAs retire first
+          mbar_wait(dfull + 2, (tl - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          const uint32_t sA = stage_wait();
+          const int slotA = it % a.stages;
+          ++it;
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            const uint32_t sb = stage_wait();
+            mma_block_ss(R0 + nhf * 128, idesc_2, sA, sb, kb == 0);
+            umma_commit(empty + it % a.stages);
+          }
+          umma_commit(empty + slotA);
+        }
+        umma_commit(dfull + 0);
+        if (tr) tr[1] = clock64();
+        for (int c = 0; c < a.nchunk; ++c) {
+          mbar_wait(hready + c, 0);
+          tc_fence_after();
+          if (tr && c == 0) tr[2] = clock64();
+          for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
+            const uint32_t sb = stage_wait();
+            mma_block_ts(R1 + nhf * 128, idesc_2, R0, c, sb, c == 0);
+            umma_commit(empty + it % a.stages);
+          }
+        }
+        umma_commit(dfull + 1);
+        if (tr) tr[3] = clock64();
+        for (int pc = 0; pc < a.np3; ++pc) {
+          const int n = min(128, a.n3pad - pc * 128);
+          const uint32_t idesc_3 = make_idesc_bf16(128, n, 0, 0);
+          for (int c = 0; c < a.nchunk; ++c, ++it) {
+            mbar_wait(hready + c, 1);
+            tc_fence_after();
+            if (tr && pc == 0 && c == 0) tr[4] = clock64();
+            const uint32_t sb = stage_wait();
+            mma_block_ts(R0 + pc * 128, idesc_3, R1, c, sb, c == 0);
+            umma_commit(empty + it % a.stages);
+          }
+        }
+        umma_commit(dfull + 2);
+        if (tr) tr[5] = clock64();
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------ epilogue warps
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int tid = e * 32 + lane;
+    uint32_t tl = 0;
+    uint32_t use0 = 0, use1 = 0;  // completed uses of the two staging slots (store mode)
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tl) {
+      const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
+      const long long m = (long long)tile * 128 + row;
+      const bool live = m < a.M;
+      long long* tr = (a.trace && blockIdx.x == 0 && tl < 16 && e == 0 && lane == 0) ? a.trace + tl * 16 + 6 : nullptr;
+#pragma unroll 1
+      for (int stg = 0; stg < 2; ++stg) {
+        const uint32_t reg = (stg ? R1 : R0) + lane_sel + 32 * half;
+        const float* sb = sbias + stg * 256 + 32 * half;
+        const __nv_bfloat16* mk = (stg ? a.mask2 : a.mask1) + m * a.nh + 32 * half;
+        mbar_wait(dfull + stg, tl & 1);
+        tc_fence_after();
+        if (stg == 0 && tl > 0) {  // the P stores of the previous tile have read the staging area
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        if (tr) tr[2 * stg] = clock64();
+        uint32_t rA[32], rB[32];
+        uint4 mA[4], mB[4];
+        auto fetch = [&](int c, uint32_t (&r)[32], uint4 (&mm)[4]) {
+          if (a.mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              mm[j] = live ? __ldg(reinterpret_cast<const uint4*>(mk + 64 * c) + j) : make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld32(reg + 64 * c, r);
+        };
+        auto emit = [&](int c, const uint32_t (&r)[32], const uint4 (&mm)[4]) {
+          uint32_t wh[16], wl[16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 oh, ol;
+            if (a.mode == 0) chain_pack8<0, NT>(r + 8 * g, sb + 64 * c + 8 * g, make_uint4(0, 0, 0, 0), oh, ol);
+            else chain_pack8<1, NT>(r + 8 * g, sb, mm[g], oh, ol);
+            wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
+            wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
+          }
+          // in place: the 32 fp32 columns just read become 16 packed hi + 16 packed lo columns
+          tmem_st16(reg + 64 * c, wh);
+          if (NT == 3) tmem_st16(reg + 64 * c + 16, wl);
+          if (a.store) {
+            const int slot = c & 1;
+            uint32_t& use = slot ? use1 : use0;
+            if (use > 0) mbar_wait(sfree + slot, (use - 1) & 1);  // the slot's previous TMA store has read it
+            uint8_t* dst = stag + slot * SLOT + row * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t off = (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst + off) = make_uint4(wh[4 * g], wh[4 * g + 1], wh[4 * g + 2], wh[4 * g + 3]);
+              if (NT == 3)
+                *reinterpret_cast<uint4*>(dst + kPlane + off) = make_uint4(wl[4 * g], wl[4 * g + 1], wl[4 * g + 2], wl[4 * g + 3]);
+            }
+            fence_proxy_async();
+            ++use;
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(hready + c);
+            if (a.store) mbar_arrive(sready + (c & 1));
+          }
+        };
+        fetch(0, rA, mA);
+#pragma unroll 1
+        for (int c = 0; c < a.nchunk; c += 2) {
+          tmem_ld_wait();
+          fetch(c + 1, rB, mB);
+          emit(c, rA, mA);
+          tmem_ld_wait();
+          if (c + 2 < a.nchunk) fetch(c + 2, rA, mA);
+          emit(c + 1, rB, mB);
+        }
+        if (tr) tr[2 * stg + 1] = clock64();
+      }
+      // E3: tap-expanded columns (region R0, <= 256 of them) -> staging -> TMA store of P
+      mbar_wait(dfull + 2, tl & 1);
+      tc_fence_after();
+      if (tr) tr[4] = clock64();
+      if (a.store) {  // both staging slots: their last TMA stores have read them
+        if (use0 > 0) mbar_wait(sfree + 0, (use0 - 1) & 1);
+        if (use1 > 0) mbar_wait(sfree + 1, (use1 - 1) & 1);
+      }
+#pragma unroll 1
+      for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
+        const int ncols = min(128, a.n3pad - slab * 128);
+        const uint32_t dsrc = R0 + slab * 128 + lane_sel;
+        const int nsplit = ((ncols / 16 + 1) / 2) * 16;
+        const int cbeg = half ? nsplit : 0, cend = half ? ncols : nsplit;
+        if (slab > 0) {
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        auto stage16 = [&](int col, const uint32_t* r) {
+          uint8_t* g = stag + (col >> 5) * kPlane + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = ((col & 31) >> 2) + j;
+            *reinterpret_cast<uint4*>(g + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        };
+        int c0 = cbeg;
+        for (; c0 + 32 <= cend; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(dsrc + c0, r);
+          tmem_ld_wait();
+          stage16(c0, r);
+          stage16(c0 + 16, r + 16);
+        }
+        if (c0 < cend) {
+          uint32_t r[16];
+          tmem_ld16(dsrc + c0, r);
+          tmem_ld_wait();
+          stage16(c0, r);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) {
+          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, stag + g * kPlane, slab * 128 + g * 32, tile * 128);
+          bulk_commit();
+        }
+      }
+      if (tr) tr[5] = clock64();
+    }
+    if (tid == 0) bulk_wait0();
+  } else if (a.store) {
+    // ------------------------------------------------------------ TMA store warp: hidden chunks -> HBM
+    if (lane == 0) {
+      uint32_t use[2] = {0, 0};
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int stg = 0; stg < 2; ++stg) {
+          for (int c = 0; c < a.nchunk; ++c) {
+            const int slot = c & 1;
+            mbar_wait(sready + slot, use[slot] & 1);
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl)
+              tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(sfree + slot);
+            ++use[slot];
+          }
+        }
+      }
+      bulk_wait0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------- col2im
 // out[b][n][pix] = sum_tap P[pix + off(tap)][tap*Cn + n]  (+ passthrough add), coalesced both ways through a
 // shared-memory transpose: phase 1 walks (pixel, n) with n fastest (contiguous in P), phase 2 walks pixels.
@@ -575,12 +931,16 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
   const size_t aux = 32 * 8 + 16 + 512 * 4;
   const size_t cap = 227 * 1024;
-  int stages = (int)((cap - aux - a.nchunk * chunk) / stage);
+  // hidden operand in tensor memory (k_rb_chain_t) unless GEMM3 needs more than one 256-column region
+  static const bool force_smem = [] { const char* e = getenv("INB_CHAIN_SMEM"); return e && e[0] == '1'; }();
+  const bool tmem_a = a.n3pad <= 256 && !force_smem;
+  const size_t fixed = tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk;
+  int stages = (int)((cap - aux - fixed) / stage);
   if (stages > 8) stages = 8;
   // the im2col block of GEMM1 stays resident while the nh/128 weight halves stream past it
   INB_CHECK(stages >= 1 + s.nh / 128, "fused ResidualBlock chain: shared memory does not fit");
   a.stages = stages;
-  const size_t smem = a.nchunk * chunk + stages * stage + aux;
+  const size_t smem = fixed + stages * stage + aux;
   ChainMaps mp{};
   for (int pl = 0; pl < 2; ++pl) {
     mp.A[pl] = make_rows_map(pl ? s.in.lo : s.in.hi, s.in.pitch, a.M, 64, 128);
@@ -600,7 +960,13 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   const double flops = 2.0 * a.M * ((double)s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
   {
     Prof pf(c, F_CONV_TC, 1, flops, 0);
-    if (NT == 3) {
+    if (tmem_a && NT == 3) {
+      INB_CUDA(cudaFuncSetAttribute(k_rb_chain_t<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rb_chain_t<3><<<grid, kChainThreads, smem, c.st>>>(mp, a);
+    } else if (tmem_a) {
+      INB_CUDA(cudaFuncSetAttribute(k_rb_chain_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_rb_chain_t<1><<<grid, kChainThreads, smem, c.st>>>(mp, a);
+    } else if (NT == 3) {
       INB_CUDA(cudaFuncSetAttribute(k_rb_chain<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_rb_chain<3><<<grid, kChainThreads, smem, c.st>>>(mp, a);
     } else {
