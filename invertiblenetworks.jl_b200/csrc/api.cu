@@ -94,11 +94,16 @@ struct inb_plan {
   double* ld = nullptr;
   // CUDA graphs of the network-level calls (slot 0 forward, 1 inverse, 2 backward): a call with the same
   // pointers and batch as the captured one replays ~1500 launches with a single cudaGraphLaunch
+  // (a caller's allocator typically cycles through a few addresses for its outputs: kGraphWays entries per
+  // slot, least recently used replaced)
+  static constexpr int kGraphWays = 4;
   struct GraphSlot {
     uint64_t key = 0;
     cudaGraphExec_t exec = nullptr;
     long long launches = 0;
-  } graphs[3];
+    unsigned long long used = 0;
+  } graphs[3][kGraphWays];
+  unsigned long long graph_clock = 0;
   cudaStream_t capture_stream = nullptr;
 };
 
@@ -452,7 +457,16 @@ static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& e
     enqueue(c);
     return;
   }
-  inb_plan::GraphSlot& g = p->graphs[slot];
+  inb_plan::GraphSlot* gp = nullptr;
+  for (auto& w : p->graphs[slot])
+    if (w.exec && w.key == key) gp = &w;
+  if (!gp) {  // least recently used way
+    gp = &p->graphs[slot][0];
+    for (auto& w : p->graphs[slot])
+      if (w.used < gp->used) gp = &w;
+  }
+  inb_plan::GraphSlot& g = *gp;
+  g.used = ++p->graph_clock;
   if (g.exec == nullptr || g.key != key) {
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (!p->capture_stream) INB_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
@@ -528,8 +542,9 @@ int inb_glow_plan_create(const inb_glow_desc* desc, inb_plan** out) {
 int inb_glow_plan_destroy(inb_plan* p) {
   return guarded([&] {
     if (!p) return;
-    for (auto& g : p->graphs)
-      if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& slot : p->graphs)
+      for (auto& g : slot)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;

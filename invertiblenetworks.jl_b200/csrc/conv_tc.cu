@@ -195,7 +195,9 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
   const int z = (int)t;
   const float* p0 = in0 + b * in0_bs + pix;
   const float* p1 = in1 ? in1 + b * in1_bs + pix - (long long)c0 * px : nullptr;
-  int tap = 0, ch = 0;      // running (tap, channel) of column k
+  // blockIdx.y = 64-column chunk: more parallelism when the batch shard is small, shorter threads
+  const int kc = blockIdx.y * 64;
+  int tap = kc / C, ch = kc - (kc / C) * C;  // running (tap, channel) of column k
   bool ok = false;          // this pixel's neighbour for `tap` is inside the image
   const float* src = p0;    // running pointer: channel `ch` of that neighbour
   auto set_tap = [&]() {
@@ -206,7 +208,8 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
     src = ((c0 > 0) ? p0 : p1) + (dx + (long long)dy * W + (long long)dz * W * H);
   };
   set_tap();
-  for (int kc = 0; kc < kp; kc += 64) {
+  if (ch > 0 && tap < T) src = ((ch < c0) ? p0 : p1) + (src - ((c0 > 0) ? p0 : p1)) + (long long)ch * px;
+  {
 #pragma unroll 8
     for (int j = 0; j < 64; ++j) {
       float v = 0.f;
@@ -249,37 +252,8 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   const long long M = g.px * B;
   const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
-  k_im2col_tc<<<(unsigned)cdiv(M, kI2cThreads), kI2cThreads, 0, c.st>>>(
+  k_im2col_tc<<<dim3((unsigned)cdiv(M, kI2cThreads), (unsigned)(kp / 64)), kI2cThreads, 0, c.st>>>(
       in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M, kp, ones_col, out.hi, out.lo);
-  INB_CUDA(cudaGetLastError());
-}
-
-// dense-K weight rows for the im2col operand: out[n][tap*Cc + cc] (zero up to kp), same values as k_pack_w_tc
-__global__ void k_pack_w_dense_tc(int mode, int d0, int d1, int T, const float* __restrict__ w, int npad, int kp,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const long long n_el = (long long)npad * kp;
-  const int O = mode == PACK_CONV ? d0 : d1, Cc = mode == PACK_CONV ? d1 : d0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_el;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % kp);
-    const int n = (int)(i / kp);
-    float v = 0.f;
-    if (n < O && k < T * Cc) {
-      const int tap = k / Cc, cc = k - tap * Cc;
-      if (mode == PACK_CONV) v = w[((long long)n * d1 + cc) * T + (T - 1 - tap)];
-      else v = w[((long long)cc * d1 + n) * T + tap];
-    }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
-  }
-}
-void op_pack_w_dense_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int kp, Planes out) {
-  if (c.dry()) return;
-  const long long n = (long long)npad * kp;
-  Prof pf(c, F_PACK, 1, 0, 8.0 * n);
-  k_pack_w_dense_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(mode, d0, d1, T, w, npad, kp, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
 }
 

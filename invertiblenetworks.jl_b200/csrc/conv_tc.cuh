@@ -36,8 +36,6 @@ void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int n
 // out [M][kp] with kp = chain_kpad(T*C); `ones_col` (>= 0) is a column of ones
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
                   long long in1_bs, int C, int kp, int ones_col, Planes out);
-// weights against those rows: out [npad][kp], column tap*Cc + cc
-void op_pack_w_dense_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int npad, int kp, Planes out);
 // per-channel sum over rows of planes [M][C] -> out[C] (bias gradients)
 void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out);
 
@@ -112,7 +110,9 @@ struct ChainSpec {
 int chain_n3pad(int taps, int Cn);
 int chain_kpad(int taps, int C, int extra);  // im2col width: taps*C (+ extra columns) rounded up to 64
 bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn);
-void op_pack_wexp_tc(Ctx& c, int nh, int Cn, int T, const float* w, int n3pad, Planes out);
+// the three packed operands of one chain pass in a single launch (conv_tc_chain.cu: k_pack_chain_tc)
+void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
+                      int n3pad, const float* wc, Planes w1, Planes w2, Planes w3);
 void op_rb_chain(Ctx& c, const ChainSpec& s);
 void chain_set_trace(long long* p);
 

@@ -819,21 +819,31 @@ __global__ void __launch_bounds__(256) k_col2im(const Col2imArgs a) {
       const int y = (int)(t % a.H); t /= a.H;
       const int z = (int)(t % a.D);
       const float* base = a.P + m * a.n3pad + g * V;
-      for (int tap = 0; tap < a.taps; ++tap) {
-        int dx, dy, dz;
-        chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
-        const int xx = x + dx, yy = y + dy, zz = z + dz;
-        if (xx < 0 || xx >= a.W || yy < 0 || yy >= a.H || zz < 0 || zz >= a.D) continue;
-        const float* src = base + (dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.Cn;
-        if (V == 4) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(src));
-          acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
-        } else if (V == 2) {
-          const float2 q = __ldg(reinterpret_cast<const float2*>(src));
-          acc[0] += q.x; acc[1] += q.y;
-        } else {
-          acc[0] += __ldg(src);
+      // taps in batches of 9: all loads of a batch are issued before the first add (memory-level parallelism)
+      for (int t0 = 0; t0 < a.taps; t0 += 9) {
+        float q[9][V];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int tap = t0 + j;
+          int dx, dy, dz;
+          chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          const bool ok = tap < a.taps && xx >= 0 && xx < a.W && yy >= 0 && yy < a.H && zz >= 0 && zz < a.D;
+          const float* src = base + (dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.Cn;
+          if (V == 4) {
+            const float4 w = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[j][0] = w.x; q[j][1 % V] = w.y; q[j][2 % V] = w.z; q[j][3 % V] = w.w;
+          } else if (V == 2) {
+            const float2 w = ok ? __ldg(reinterpret_cast<const float2*>(src)) : make_float2(0.f, 0.f);
+            q[j][0] = w.x; q[j][1 % V] = w.y;
+          } else {
+            q[j][0] = ok ? __ldg(src) : 0.f;
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] += q[j][v];
       }
     }
 #pragma unroll
@@ -856,33 +866,60 @@ __global__ void __launch_bounds__(256) k_col2im(const Col2imArgs a) {
   }
 }
 
-// ---------------------------------------------------------------- tap-expanded weight packing
-// rows r = tap*Cn + n (zero rows up to n3pad), K = nh columns:  Wexp[r][c] = coefficient of hidden
-// channel c in tap `tap` of output channel n of the \nabla conv_data contraction (PACK_DATA order of
-// op_pack_w_tc: w[c][n][tap] for the reference weight w[d0 = nh][d1 = Cn][T]).
-__global__ void k_pack_wexp_tc(int nh, int Cn, int T, const float* __restrict__ w, int n3pad,
-                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const long long n_el = (long long)n3pad * nh;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_el;
+// ---------------------------------------------------------------- weight packing for one chain pass
+// One launch packs the three operands of a pass into bf16 hi/lo planes:
+//   w1 [nh][kp]     dense-K rows against the im2col operand:  column tap*C1 + c  <-  wa[n][c][T-1-tap]   (NNlib conv)
+//   w2 [nh][nh]     the 1x1 contraction + I (residual skip / '+ dY2'):  conv: wb[n][c],  data: wb[c][n]
+//   w3 [n3pad][nh]  tap-expanded rows of the \nabla conv_data contraction:  row tap*Cn + n  <-  wc[c][n][tap]
+// (wa = W1, wc = W3 in the forward pass; wa = W3, wc = W1 in the backward pass; reference layout w[d0][d1][T])
+struct PackChainArgs {
+  int nh, T, C1, kp, Cn, n3pad, w2_data;
+  const float *wa, *wb, *wc;
+  __nv_bfloat16 *w1h, *w1l, *w2h, *w2l, *w3h, *w3l;
+};
+__global__ void k_pack_chain_tc(const PackChainArgs a) {
+  const long long n1 = (long long)a.nh * a.kp, n2 = (long long)a.nh * a.nh, n3 = (long long)a.n3pad * a.nh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2 + n3;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % nh);
-    const int r = (int)(i / nh);
     float v = 0.f;
-    if (r < T * Cn) {
-      const int tap = r / Cn, n = r - tap * Cn;
-      v = w[((long long)c * Cn + n) * T + tap];
+    __nv_bfloat16 *dh, *dl;
+    long long o;
+    if (i < n1) {
+      o = i;
+      const int k = (int)(i % a.kp), n = (int)(i / a.kp);
+      if (k < a.T * a.C1) {
+        const int tap = k / a.C1, cc = k - tap * a.C1;
+        v = a.wa[((long long)n * a.C1 + cc) * a.T + (a.T - 1 - tap)];
+      }
+      dh = a.w1h; dl = a.w1l;
+    } else if (i < n1 + n2) {
+      o = i - n1;
+      const int cc = (int)(o % a.nh), n = (int)(o / a.nh);
+      v = a.w2_data ? a.wb[(long long)cc * a.nh + n] : a.wb[(long long)n * a.nh + cc];
+      if (n == cc) v += 1.f;
+      dh = a.w2h; dl = a.w2l;
+    } else {
+      o = i - n1 - n2;
+      const int c = (int)(o % a.nh), r = (int)(o / a.nh);
+      if (r < a.T * a.Cn) {
+        const int tap = r / a.Cn, n = r - tap * a.Cn;
+        v = a.wc[((long long)c * a.Cn + n) * a.T + tap];
+      }
+      dh = a.w3h; dl = a.w3l;
     }
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    dh[o] = h;
+    dl[o] = l;
   }
 }
-void op_pack_wexp_tc(Ctx& c, int nh, int Cn, int T, const float* w, int n3pad, Planes out) {
+void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
+                      int n3pad, const float* wc, Planes w1, Planes w2, Planes w3) {
   if (c.dry()) return;
-  const long long n = (long long)n3pad * nh;
+  PackChainArgs a{nh, T, C1, kp, Cn, n3pad, w2_data, wa, wb, wc, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo};
+  const long long n = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
   Prof pf(c, F_PACK, 1, 0, 8.0 * n);
-  k_pack_wexp_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(nh, Cn, T, w, n3pad, out.hi, out.lo);
+  k_pack_chain_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(a);
   INB_CUDA(cudaGetLastError());
 }
 

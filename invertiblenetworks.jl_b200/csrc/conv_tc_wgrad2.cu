@@ -241,7 +241,9 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   INB_CHECK(stages >= 2, "tensor-core wgrad: stage of %u bytes does not fit", a.stage_bytes);
   INB_CHECK((size_t)stages * a.stage_bytes >= (size_t)(nqmax / 32) * 16384, "tensor-core wgrad: staging does not fit");
   a.stages = stages;
-  const int ctas = std::max(1, 148 / ng);
+  // split-K over the SMs, but at least 16 k-blocks (512 pixels) per CTA: every CTA costs a partial tile that the
+  // reduction has to read back, which dominates when the batch shard is small
+  const int ctas = std::max(1, std::min(148 / ng, a.nblocks / 16));
   a.blocks_per_cta = (int)cdiv(a.nblocks, ctas);
   const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);  // every CTA owns at least one block
   // scratch: partial tiles [ng][gx][np][nqmax] and partial bias sums [gx][np]

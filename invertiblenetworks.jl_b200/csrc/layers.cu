@@ -186,9 +186,8 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
     const int n3pad = chain_n3pad(T1, s.Cout);
     Planes W1 = planes_new(c, nh, kp), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
-    op_pack_w_dense_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, kp, W1);
-    op_pack_w_tc(c, PACK_CONV, nh, nh, 1, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
-    op_pack_wexp_tc(c, nh, s.Cout, T1, p.W3, n3pad, W3);
+    // conv(X, W1) | W2 + I (the skip of :125) | \nabla conv_data(., W3) tap-expanded
+    op_pack_chain_tc(c, nh, T1, Cin, kp, p.W1, p.W2, 0, s.Cout, n3pad, p.W3, W1, W2, W3);
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
@@ -249,9 +248,8 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     Planes W3c = planes_new(c, nh, kp), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
     Planes dcol = planes_new(c, M, kp);
     op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol);
-    op_pack_w_dense_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, kp, W3c);   // :151
-    op_pack_w_tc(c, PACK_DATA, nh, nh, 1, p.W2, nh, nh, W2d, 1);         // :155, + I: the '+ dY2'
-    op_pack_wexp_tc(c, nh, Cin, T1, p.W1, n3pad, W1e);                   // :162
+    // conv(dY3, W3) :151 | \nabla conv_data(., W2) + I (the '+ dY2' of :155) | \nabla conv_data(., W1) tap-expanded :162
+    op_pack_chain_tc(c, nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = dcol; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
