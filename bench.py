@@ -212,8 +212,8 @@ def main():
         inb200.dp.broadcast_params(G.flat_params, src=0)
         G._mark_initialized()
 
-    def step_device():
-        Z, ld = G.forward(X)
+    def step_device(Xin=None):
+        Z, ld = G.forward(X if Xin is None else Xin)
         nll, dZ = inb200.nll_grad(Z, B)
         G.backward(dZ, Z)
         inb200.clear_grad(G)
@@ -221,14 +221,44 @@ def main():
             inb200.dp.allreduce_grads(G.flat_grads)
         return nll, ld
 
+    # End-to-end loop (what a training script does): every step's batch comes from pinned host memory and the
+    # step's loss goes back to the host, which waits for it before the next step.  The input copy of step k+1
+    # is issued on a copy stream while step k computes (two device buffers), like any prefetching data loader;
+    # all K copies and K loss reads happen inside the timed region.
     loss_host = torch.empty(2).pin_memory()
+    Xbuf = [X, torch.empty_like(X)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"k": 0, "pending": False}
 
-    def step_e2e():
-        X.copy_(X_host, non_blocking=True)
-        nll, ld = step_device()
+    def prefetch(buf):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[buf])
+            Xbuf[buf].copy_(X_host, non_blocking=True)
+            copied[buf].record(copy_stream)
+
+    def step_e2e(last=False):
+        k = e2e_state["k"]
+        buf = k & 1
+        if not e2e_state["pending"]:
+            prefetch(buf)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(copied[buf])
+        Z, ld = G.forward(Xbuf[buf])
+        consumed[buf].record(cur)  # backward recomputes X from Z: the input buffer is free after forward
+        if not last:
+            prefetch(buf ^ 1)
+        e2e_state["pending"] = not last
+        nll, dZ = inb200.nll_grad(Z, B)
+        G.backward(dZ, Z)
+        inb200.clear_grad(G)
+        if world > 1:
+            inb200.dp.allreduce_grads(G.flat_grads)
         loss_host[0:1].copy_(nll.reshape(1), non_blocking=True)
         loss_host[1:2].copy_(ld.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
+        e2e_state["k"] = k + 1
         return float(loss_host[0] - loss_host[1])
 
     def barrier():
@@ -236,12 +266,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    def timed(fn, n, mark_last=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            fn()
+        for i in range(n):
+            if mark_last:
+                fn(last=(i == n - 1))
+            else:
+                fn()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -280,9 +313,21 @@ def main():
     host_enqueue_ms = (time.perf_counter() - t0) * 1e3 / steps
     barrier()
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, steps)
-    f_last = step_e2e()
+    step_e2e(last=True)
+    step_e2e(last=True)  # both input buffers have been through the graph cache once
+    g0 = G.graph_stats()
+    ms_e2e = timed(step_e2e, steps, mark_last=True)
+    g1 = G.graph_stats()
+    f_last = step_e2e(last=True)
+    # host -> device bandwidth of this box for the step's input (explains e2e - value when the link is slow)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(3):
+        Xbuf[1].copy_(X_host, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * X_host.numel() * 4 / (h0.elapsed_time(h1) / 1e3) / 1e9
 
     if rank != 0:
         if world > 1:
@@ -321,8 +366,10 @@ def main():
         "data": "synthetic", "config": workload_config(cfg, args.config, gb, args.precision),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": X_host.numel() * 4 * world,
-                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / steps, "loss": f_last},
+                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / steps, "loss": f_last,
+                "h2d_gbs_measured": h2d_gbs, "input_prefetch": "copy of step k+1 overlaps step k (copy stream)"},
         "gpu_launches": launches, "host_enqueue_ms_per_step": host_enqueue_ms,
+        "graphs_in_e2e_region": {k: g1[k] - g0[k] for k in g1},
         "roofline": roof,
         "model_flops": {"rb_forward_gflop_per_sample": F / 1e9, "fwd_bwd_gflop_per_sample": 4 * F / 1e9,
                         "useful_tflops": 4 * F * value / 1e12, "frac_of_tensor_peak": 4 * F * value / 1e12 / pk["tensor"],

@@ -169,9 +169,13 @@ int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, voi
  * and its algorithmic flops / bytes are summed; inb_prof_get synchronises on the recorded events. */
 long long inb_launch_count(void);
 int inb_prof_enable(int on);
-/* diagnostics: device buffer of 16 x 16 int64 that receives per-tile phase timestamps (SM clock) of CTA 0 of the
-   fused ResidualBlock kernel (MMA issuer: slots 0-5, first epilogue warp: slots 6-11); NULL switches it off */
+/* diagnostics: device buffer of 4 x 32 x 16 int64; launch i of the fused ResidualBlock kernel after this call
+   writes block i % 4: per-tile phase timestamps (SM clock) of CTA 0 (MMA issuer: slots 0-5, first epilogue
+   warp: slots 6-11); NULL switches it off */
 int inb_debug_chain_trace(void* dev_buf);
+/* CUDA-graph replay accounting of a plan's network-level calls: graphs captured, graph launches, and calls
+   launched kernel by kernel because the caller's buffer addresses kept changing (see api.cu run_graphed) */
+int inb_glow_graph_stats(const inb_plan* plan, long long* captures, long long* replays, long long* direct);
 int inb_prof_reset(void);
 int inb_prof_num(void);
 int inb_prof_get(int index, char* name, int name_len, long long* launches, long long* scopes, double* ms,

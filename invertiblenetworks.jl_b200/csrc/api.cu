@@ -2,6 +2,7 @@
 // and the network drivers that walk the L x K flow steps inside the library.
 #include "../../include/inb200.h"
 #include "glow.cuh"
+#include <mutex>
 
 #include <cstring>
 #include <memory>
@@ -40,14 +41,35 @@ static int guarded(F&& f) {
   }
 }
 
-// stream-ordered temporary arena for the layer-level entry points
+// stream-ordered temporary arena for the layer-level entry points.  The library keeps its own memory pool per
+// device with an unlimited release threshold: the default pool hands its pages back to the driver at every
+// synchronisation, which made each layer-level call re-map its whole workspace (tens of ms for a cfg2 block).
+static cudaMemPool_t temp_pool() {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  INB_CUDA(cudaGetDevice(&dev));
+  INB_CHECK(dev >= 0 && dev < 64, "device index out of range");
+  std::lock_guard<std::mutex> lk(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    INB_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+    unsigned long long keep = ~0ull;
+    INB_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  return pools[dev];
+}
 struct TempArena {
   Arena ar;
   cudaStream_t st;
   TempArena(cudaStream_t s) : st(s) {}
   void reserve(size_t bytes) {
     void* p = nullptr;
-    INB_CUDA(cudaMallocAsync(&p, bytes + 512, st));
+    INB_CUDA(cudaMallocFromPoolAsync(&p, bytes + 512, temp_pool(), st));
     ar.base = (char*)p;
     ar.cap = bytes + 512;
     ar.off = 0;
@@ -96,7 +118,7 @@ struct inb_plan {
   // pointers and batch as the captured one replays ~1500 launches with a single cudaGraphLaunch
   // (a caller's allocator typically cycles through a few addresses for its outputs: kGraphWays entries per
   // slot, least recently used replaced)
-  static constexpr int kGraphWays = 4;
+  static constexpr int kGraphWays = 8;
   struct GraphSlot {
     uint64_t key = 0;
     cudaGraphExec_t exec = nullptr;
@@ -104,6 +126,11 @@ struct inb_plan {
     unsigned long long used = 0;
   } graphs[3][kGraphWays];
   unsigned long long graph_clock = 0;
+  // per call type: hit (0) / miss (1) history of the last 32 calls, and counters for inb_graph_stats.  A caller
+  // whose allocator never repeats an address combination would otherwise pay a capture + instantiate (tens
+  // of ms) on every call: once the ways are full and misses keep coming, such calls are launched directly.
+  uint32_t graph_hist[3] = {0, 0, 0};
+  long long graph_captures = 0, graph_replays = 0, graph_direct = 0;
   cudaStream_t capture_stream = nullptr;
 };
 
@@ -458,9 +485,20 @@ static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& e
     return;
   }
   inb_plan::GraphSlot* gp = nullptr;
-  for (auto& w : p->graphs[slot])
+  bool full = true;
+  for (auto& w : p->graphs[slot]) {
     if (w.exec && w.key == key) gp = &w;
-  if (!gp) {  // least recently used way
+    if (!w.exec) full = false;
+  }
+  p->graph_hist[slot] = (p->graph_hist[slot] << 1) | (gp ? 0u : 1u);
+  if (!gp) {
+    if (full && __builtin_popcount(p->graph_hist[slot]) > 8) {  // thrashing: no point in capturing this call
+      Ctx c = call_ctx(p, stream);
+      enqueue(c);
+      ++p->graph_direct;
+      return;
+    }
+    // least recently used way
     gp = &p->graphs[slot][0];
     for (auto& w : p->graphs[slot])
       if (w.used < gp->used) gp = &w;
@@ -492,9 +530,11 @@ static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& e
       fail(2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     }
     g.key = key;
+    ++p->graph_captures;
   }
   INB_CUDA(cudaGraphLaunch(g.exec, st));
   launch_count_add(g.launches);
+  ++p->graph_replays;
 }
 
 extern "C" {
@@ -548,6 +588,15 @@ int inb_glow_plan_destroy(inb_plan* p) {
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;
+  });
+}
+
+int inb_glow_graph_stats(const inb_plan* p, long long* captures, long long* replays, long long* direct) {
+  return guarded([&] {
+    INB_CHECK(p != nullptr, "null plan");
+    if (captures) *captures = p->graph_captures;
+    if (replays) *replays = p->graph_replays;
+    if (direct) *direct = p->graph_direct;
   });
 }
 

@@ -925,7 +925,8 @@ void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, co
 
 // ---------------------------------------------------------------- host side
 static long long* g_chain_trace = nullptr;
-void chain_set_trace(long long* p) { g_chain_trace = p; }
+static int g_chain_trace_launch = 0;  // successive launches write successive 32 x 16 blocks (4 of them, cyclic)
+void chain_set_trace(long long* p) { g_chain_trace = p; g_chain_trace_launch = 0; }
 
 int chain_n3pad(int taps, int Cn) { return (taps * Cn + 15) / 16 * 16; }
 
@@ -964,7 +965,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.bias1 = s.bias1; a.bias2 = s.bias2;
   a.mask1 = s.mask1.hi; a.mask2 = s.mask2.hi;
   a.P = s.P;
-  a.trace = g_chain_trace;
+  a.trace = g_chain_trace ? g_chain_trace + (size_t)(g_chain_trace_launch++ % 4) * 512 : nullptr;
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
   const size_t aux = 32 * 8 + 16 + 512 * 4;
   const size_t cap = 227 * 1024;

@@ -426,6 +426,15 @@ class _GlowBase:
         self._plan, self._plan_key = plan, key + (B,)
         return plan
 
+    def graph_stats(self):
+        """{captures, replays, direct} of the plan's CUDA-graph replay (diagnostics for bench.py)."""
+        import ctypes
+        if getattr(self, "_plan", None) is None:
+            return {"captures": 0, "replays": 0, "direct": 0}
+        a, b, c = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        _l.call("inb_glow_graph_stats", self._plan, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"captures": a.value, "replays": b.value, "direct": c.value}
+
     def _free_plan(self):
         if getattr(self, "_plan", None) is not None:
             _l.load().inb_glow_plan_destroy(self._plan)

@@ -66,6 +66,7 @@ SIGNATURES = {
     "inb_launch_count": (LL, []),
     "inb_prof_enable": (I, [I]),
     "inb_debug_chain_trace": (I, [P]),
+    "inb_glow_graph_stats": (I, [P, C.POINTER(LL), C.POINTER(LL), C.POINTER(LL)]),
     "inb_prof_reset": (I, []),
     "inb_prof_num": (I, []),
     "inb_prof_get": (I, [I, C.c_char_p, I, C.POINTER(LL), C.POINTER(LL), C.POINTER(C.c_double),
