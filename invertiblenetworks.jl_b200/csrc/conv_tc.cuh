@@ -99,7 +99,8 @@ struct ChainSpec {
   int Cn;             // real output channels of the last contraction
   int mode;
   const float *bias1, *bias2;
-  Planes mask1, mask2;
+  const uint32_t *mask1, *mask2;  // mode 1: relu-grad masks of the two epilogues, bit planes [M][nh/32]
+  uint32_t *bits1, *bits2;        // mode 0 with o1/o2: the bit planes this pass writes (signs of Y1 / Y2)
   Planes o1, o2;      // hidden outputs in HBM (hi == nullptr: not stored)
   float* P;           // scratch [M][chain_n3pad(taps, Cn)]
   // output of col2im, same meaning as ConvTcSpec mode 1

@@ -48,8 +48,12 @@ struct ChainArgs {
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
-  const __nv_bfloat16 *mask1, *mask2;  // hi planes [M][nh] whose sign bits are the masks of E1 / E2
+  // relu-grad masks as bit planes [M][nh/32] uint32: word half*nchunk + c of a row holds channels 64c+32half .. +31
+  // (bit set = pre-activation negative).  mode 1 reads mask1 / mask2 in E1 / E2; mode 0 with store writes bits1 / bits2.
+  const uint32_t *mask1, *mask2;
+  uint32_t *bits1, *bits2;
   float* P;
+  int exp;                // experiment bits (INB_CHAIN_EXP; timing studies only, results are garbage): 1 no weight TMA, 2 no mask loads
   long long* trace;       // diagnostics: per-tile phase timestamps of CTA 0 (inb_debug_chain_trace), nullable
 };
 
@@ -63,10 +67,12 @@ __device__ __forceinline__ void chain_tap_offset(int tap, int ksz, int D, int& d
   dz = (D > 1) ? tap / 9 - 1 : 0;
 }
 
-// 8 accumulator columns -> packed bf16 hi / lo words
-template <int MODE, int NT>
-__device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint4 mh, uint4& oh, uint4& ol) {
-  const uint32_t mm[4] = {mh.x, mh.y, mh.z, mh.w};
+// 8 accumulator columns -> packed bf16 hi / lo words.  MODE 0: + bias, ReLU; when BITS the signs of the 8
+// pre-activations go to bits [sh, sh+8) of `bits` (the _relugrad mask of activation_functions.jl:84, kept as a bit
+// plane).  MODE 1: columns whose bit in `mbits` (same numbering) is set are zeroed.
+template <int MODE, int NT, bool BITS>
+__device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint32_t mbits, int sh, uint32_t& bits,
+                                            uint4& oh, uint4& ol) {
   float bias[8];
   if (MODE == 0) {
     const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
@@ -77,17 +83,15 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-    uint32_t sign = 0;
     if (MODE == 0) {
       a += bias[2 * j];
       b += bias[2 * j + 1];
-      // relu(x) = 0 is stored as -0.0 when x < 0: the sign bit of the hi plane is the _relugrad mask
-      sign = ((__float_as_uint(a) >> 16) & 0x8000u) | (__float_as_uint(b) & 0x80000000u);
+      if (BITS) bits |= ((__float_as_uint(a) >> 31) << (sh + 2 * j)) | ((__float_as_uint(b) >> 31) << (sh + 2 * j + 1));
       a = fmaxf(a, 0.f);
       b = fmaxf(b, 0.f);
     } else {
-      if (mm[j] & 0x00008000u) a = 0.f;
-      if (mm[j] & 0x80000000u) b = 0.f;
+      if ((mbits >> (sh + 2 * j)) & 1u) a = 0.f;
+      if ((mbits >> (sh + 2 * j + 1)) & 1u) b = 0.f;
     }
     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
     uint32_t h = *reinterpret_cast<uint32_t*>(&h2);
@@ -98,7 +102,7 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
     } else {
       pl[j] = 0;
     }
-    ph[j] = h | sign;
+    ph[j] = h;
   }
   oh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
   ol = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -300,7 +304,9 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t dsrc = (stg ? R1 : R0) + lane_sel + 32 * half;
         const float* sb = sbias + stg * 256 + 32 * half;
-        const __nv_bfloat16* mk = (stg ? a.mask2 : a.mask1) + m * a.nh + 32 * half;
+        const long long mrow = m * (a.nh >> 5) + half * a.nchunk;
+        const uint32_t* mk = (stg ? a.mask2 : a.mask1) + mrow;
+        uint32_t* bo = (stg ? a.bits2 : a.bits1) + mrow;
         const bool wait_store = a.store && (tl > 0 || stg > 0);
         mbar_wait(dfull + stg, tl & 1);
         tc_fence_after();
@@ -312,27 +318,29 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         // software pipeline over the 64-channel chunks: the TMEM (and mask) loads of chunk c+1 are in flight
         // while chunk c is converted and written to shared memory
         uint32_t rA[32], rB[32];
-        uint4 mA[4], mB[4];
-        auto fetch = [&](int c, uint32_t (&r)[32], uint4 (&mm)[4]) {
-          if (a.mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              mm[j] = live ? __ldg(reinterpret_cast<const uint4*>(mk + 64 * c) + j) : make_uint4(0, 0, 0, 0);
-          }
+        uint32_t mA = 0, mB = 0;
+        auto fetch = [&](int c, uint32_t (&r)[32], uint32_t& mm) {
+          if (a.mode == 1) mm = live ? __ldg(mk + c) : 0u;
           tmem_ld32(dsrc + 64 * c, r);
         };
-        auto emit = [&](int c, const uint32_t (&r)[32], const uint4 (&mm)[4]) {
+        auto emit = [&](int c, const uint32_t (&r)[32], const uint32_t mm) {
           if (wait_store) mbar_wait(stdone + c, stg ^ 1);  // the chunk's previous TMA store has read it
           uint8_t* dst = hbuf + (size_t)c * CHUNK + row * 128;
+          uint32_t bits = 0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 oh, ol;
-            if (a.mode == 0) chain_pack8<0, NT>(r + 8 * g, sb + 64 * c + 8 * g, make_uint4(0, 0, 0, 0), oh, ol);
-            else chain_pack8<1, NT>(r + 8 * g, sb, mm[g], oh, ol);
+            if (a.mode == 0) {
+              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+            } else {
+              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, 8 * g, bits, oh, ol);
+            }
             const uint32_t off = (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst + off) = oh;
             if (NT == 3) *reinterpret_cast<uint4*>(dst + kPlane + off) = ol;
           }
+          if (a.mode == 0 && a.store && live) bo[c] = bits;
           fence_proxy_async();  // generic-proxy writes -> visible to the MMA / TMA (async proxy)
           tc_fence_before();
           __syncwarp();
@@ -522,16 +530,18 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         }
         for (int c = 0; c < a.nchunk; ++c) {
           for (int nhf = 0; nhf < a.nh / 128; ++nhf, ++it) {
-            uint8_t* st = acquire(NP * kPlane);
+            uint8_t* st = acquire((a.exp & 1) ? 0 : NP * kPlane);
             uint64_t* fb = full + it % a.stages;
+            if (a.exp & 1) continue;
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W2[pl], fb, st + pl * kPlane, c * 64, nhf * 128);
           }
         }
         for (int pc = 0; pc < a.np3; ++pc) {
           for (int c = 0; c < a.nchunk; ++c, ++it) {
-            uint8_t* st = acquire(NP * kPlane);
+            uint8_t* st = acquire((a.exp & 1) ? 0 : NP * kPlane);
             uint64_t* fb = full + it % a.stages;
+            if (a.exp & 1) continue;
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl) tma_load_2d(&maps.W3[pl], fb, st + pl * kPlane, c * 64, pc * 128);
           }
@@ -544,10 +554,13 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       const uint32_t idesc_2 = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
       uint32_t it = 0, tl = 0;
+      long long twait = 0;
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % a.stages;
         const uint32_t ph = (it / a.stages) & 1;
+        const long long t0 = a.trace ? clock64() : 0;
         mbar_wait(full + s, ph);
+        if (a.trace) twait += clock64() - t0;
         tc_fence_after();
         return smem_u32(ring + (size_t)s * STAGE);
       };
@@ -597,7 +610,8 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           umma_commit(empty + slotA);
         }
         umma_commit(dfull + 0);
-        if (tr) tr[1] = clock64();
+        if (tr) { tr[1] = clock64(); tr[12] = twait; }
+        twait = 0;
         for (int c = 0; c < a.nchunk; ++c) {
           mbar_wait(hready + c, 0);
           tc_fence_after();
@@ -609,7 +623,8 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           }
         }
         umma_commit(dfull + 1);
-        if (tr) tr[3] = clock64();
+        if (tr) { tr[3] = clock64(); tr[13] = twait; }
+        twait = 0;
         for (int pc = 0; pc < a.np3; ++pc) {
           const int n = min(128, a.n3pad - pc * 128);
           const uint32_t idesc_3 = make_idesc_bf16(128, n, 0, 0);
@@ -623,7 +638,8 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           }
         }
         umma_commit(dfull + 2);
-        if (tr) tr[5] = clock64();
+        if (tr) { tr[5] = clock64(); tr[14] = twait; }
+        twait = 0;
       }
     }
   } else if (warp < 10) {
@@ -645,7 +661,9 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t reg = (stg ? R1 : R0) + lane_sel + 32 * half;
         const float* sb = sbias + stg * 256 + 32 * half;
-        const __nv_bfloat16* mk = (stg ? a.mask2 : a.mask1) + m * a.nh + 32 * half;
+        const long long mrow = m * (a.nh >> 5) + half * a.nchunk;
+        const uint32_t* mk = (stg ? a.mask2 : a.mask1) + mrow;
+        uint32_t* bo = (stg ? a.bits2 : a.bits1) + mrow;
         mbar_wait(dfull + stg, tl & 1);
         tc_fence_after();
         if (stg == 0 && tl > 0) {  // the P stores of the previous tile have read the staging area
@@ -654,28 +672,30 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         }
         if (tr) tr[2 * stg] = clock64();
         uint32_t rA[32], rB[32];
-        uint4 mA[4], mB[4];
-        auto fetch = [&](int c, uint32_t (&r)[32], uint4 (&mm)[4]) {
-          if (a.mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              mm[j] = live ? __ldg(reinterpret_cast<const uint4*>(mk + 64 * c) + j) : make_uint4(0, 0, 0, 0);
-          }
+        uint32_t mA = 0, mB = 0;
+        auto fetch = [&](int c, uint32_t (&r)[32], uint32_t& mm) {
+          if (a.mode == 1) mm = (live && !(a.exp & 2)) ? __ldg(mk + c) : 0u;
           tmem_ld32(reg + 64 * c, r);
         };
-        auto emit = [&](int c, const uint32_t (&r)[32], const uint4 (&mm)[4]) {
+        auto emit = [&](int c, const uint32_t (&r)[32], const uint32_t mm) {
           uint32_t wh[16], wl[16];
+          uint32_t bits = 0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 oh, ol;
-            if (a.mode == 0) chain_pack8<0, NT>(r + 8 * g, sb + 64 * c + 8 * g, make_uint4(0, 0, 0, 0), oh, ol);
-            else chain_pack8<1, NT>(r + 8 * g, sb, mm[g], oh, ol);
+            if (a.mode == 0) {
+              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+            } else {
+              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, 8 * g, bits, oh, ol);
+            }
             wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
             wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
           }
           // in place: the 32 fp32 columns just read become 16 packed hi + 16 packed lo columns
           tmem_st16(reg + 64 * c, wh);
           if (NT == 3) tmem_st16(reg + 64 * c + 16, wl);
+          if (a.mode == 0 && a.store && live) bo[c] = bits;
           if (a.store) {
             const int slot = c & 1;
             uint32_t& use = slot ? use1 : use0;
@@ -963,8 +983,13 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.mode = s.mode;
   a.store = (s.o1.hi != nullptr) ? 1 : 0;
   a.bias1 = s.bias1; a.bias2 = s.bias2;
-  a.mask1 = s.mask1.hi; a.mask2 = s.mask2.hi;
+  a.mask1 = s.mask1; a.mask2 = s.mask2;
+  a.bits1 = s.bits1; a.bits2 = s.bits2;
+  INB_CHECK(s.mode == 0 || (s.mask1 && s.mask2), "fused ResidualBlock chain: the backward pass needs both masks");
+  INB_CHECK(!(s.mode == 0 && s.o1.hi) || (s.bits1 && s.bits2), "fused ResidualBlock chain: a storing forward pass writes the mask bit planes");
   a.P = s.P;
+  static const int chain_exp = [] { const char* e = getenv("INB_CHAIN_EXP"); return e ? atoi(e) : 0; }();
+  a.exp = chain_exp;
   a.trace = g_chain_trace ? g_chain_trace + (size_t)(g_chain_trace_launch++ % 4) * 512 : nullptr;
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
   const size_t aux = 32 * 8 + 16 + 512 * 4;

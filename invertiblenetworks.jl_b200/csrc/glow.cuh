@@ -31,6 +31,9 @@ struct RBHidden {
   // tensor-core path: the same three buffers hold bf16 hi/lo planes [M][nh]; xin is the padded
   // bf16 copy of the block input made by rb_forward (lives in the caller's arena scope)
   Planes xin{nullptr, nullptr, 0};
+  // fused-chain path: relu-grad masks of Y1 / Y2 as bit planes [M][nh/32], written by the storing forward pass
+  uint32_t* bm1 = nullptr;
+  uint32_t* bm2 = nullptr;
 };
 
 // layer_residual_block.jl:119-134, output = PRE-activation Y3 (B, Cout, px) compact; the consumers

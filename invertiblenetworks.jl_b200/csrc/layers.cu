@@ -181,6 +181,10 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     // block input outlive this call: the weight gradient of conv1 reads them again.
     const int kp = chain_kpad(T1, Cin, 0);
     h.xin = planes_new(c, M, kp);
+    if (h.G) {  // the mask bit planes outlive this call as well (rb_backward_tc reads them)
+      h.bm1 = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes((size_t)M * (nh / 32) * 4));
+      h.bm2 = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes((size_t)M * (nh / 32) * 4));
+    }
     op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, -1, h.xin);
     size_t m = c.ar->mark();
     Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
@@ -192,7 +196,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
     cs.mode = 0; cs.bias1 = p.b1; cs.bias2 = p.b2;
-    if (h.G) { cs.o1 = H1; cs.o2 = H2; }
+    if (h.G) { cs.o1 = H1; cs.o2 = H2; cs.bits1 = h.bm1; cs.bits2 = h.bm2; }
     cs.P = c.ar->f32((size_t)M * n3pad);
     cs.out0 = Y3; cs.out0_bs = (long long)s.Cout * px; cs.n0 = s.Cout;
     cs.add_n = 1 << 30;
@@ -253,7 +257,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = dcol; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
-    cs.mode = 1; cs.mask1 = H2; cs.mask2 = H1;                           // :154, :161
+    cs.mode = 1; cs.mask1 = h.bm2; cs.mask2 = h.bm1;                     // :154, :161
     cs.o1 = G2; cs.o2 = G1;
     cs.P = c.ar->f32((size_t)M * n3pad);
     cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;

@@ -31,4 +31,5 @@ for li, title in enumerate(["forward (no store)", "recompute (stores H1, H2)", "
         if r[0].item() == 0:
             break
         v = [(x.item() - t0) for x in r[:12]]
-        print(" ".join(str(x).rjust(8) for x in v[:6]) + "        | " + " ".join(str(x).rjust(8) for x in v[6:12]))
+        print(" ".join(str(x).rjust(8) for x in v[:6]) + "        | " + " ".join(str(x).rjust(8) for x in v[6:12]),
+              "| TMA waits G1/G2/G3", r[12].item(), r[13].item(), r[14].item())
