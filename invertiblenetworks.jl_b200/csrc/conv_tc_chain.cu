@@ -48,7 +48,7 @@ struct ChainArgs {
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
-  // relu-grad masks as bit planes [M][nh/32] uint32: word half*nchunk + c of a row holds channels 64c+32half .. +31
+  // relu-grad masks as bit planes [M][nh/32] uint32 in channel order: bit (ch & 31) of word (ch >> 5) of a row
   // (bit set = pre-activation negative).  mode 1 reads mask1 / mask2 in E1 / E2; mode 0 with store writes bits1 / bits2.
   const uint32_t *mask1, *mask2;
   uint32_t *bits1, *bits2;
@@ -67,11 +67,16 @@ __device__ __forceinline__ void chain_tap_offset(int tap, int ksz, int D, int& d
   dz = (D > 1) ? tap / 9 - 1 : 0;
 }
 
+// Bit position of value j (0..7) of 8-column group g inside a 16- or 32-bit mask word: the signs are shifted in with one
+// funnel shift per value, so within each group of 8 the FIRST value lands in the HIGHEST bit.  Groups 0 / 1 are the
+// high / low byte of the low half-word, groups 2 / 3 of the high half-word (16-wide and 32-wide kernels agree).
+__device__ __forceinline__ constexpr int chain_bit_base(int g) { return ((g & 1) ? 0 : 8) + (g >> 1) * 16; }
+
 // 8 accumulator columns -> packed bf16 hi / lo words.  MODE 0: + bias, ReLU; when BITS the signs of the 8
-// pre-activations go to bits [sh, sh+8) of `bits` (the _relugrad mask of activation_functions.jl:84, kept as a bit
-// plane).  MODE 1: columns whose bit in `mbits` (same numbering) is set are zeroed.
+// pre-activations are merged into `bits` (the _relugrad mask of activation_functions.jl:84, kept as a bit plane).
+// MODE 1: columns whose bit in `mbits` is set are zeroed.  g = index of the 8-column group inside the mask word.
 template <int MODE, int NT, bool BITS>
-__device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint32_t mbits, int sh, uint32_t& bits,
+__device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint32_t mbits, int g, uint32_t& bits,
                                             uint4& oh, uint4& ol) {
   float bias[8];
   if (MODE == 0) {
@@ -79,19 +84,24 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
     bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
     bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
   }
+  const int base = chain_bit_base(g);
   uint32_t ph[4], pl[4];
+  uint32_t b8 = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
     if (MODE == 0) {
       a += bias[2 * j];
       b += bias[2 * j + 1];
-      if (BITS) bits |= ((__float_as_uint(a) >> 31) << (sh + 2 * j)) | ((__float_as_uint(b) >> 31) << (sh + 2 * j + 1));
+      if (BITS) {
+        b8 = __funnelshift_l(__float_as_uint(a), b8, 1);  // (b8 << 1) | sign(a)
+        b8 = __funnelshift_l(__float_as_uint(b), b8, 1);
+      }
       a = fmaxf(a, 0.f);
       b = fmaxf(b, 0.f);
     } else {
-      if ((mbits >> (sh + 2 * j)) & 1u) a = 0.f;
-      if ((mbits >> (sh + 2 * j + 1)) & 1u) b = 0.f;
+      if ((mbits >> (base + 7 - 2 * j)) & 1u) a = 0.f;
+      if ((mbits >> (base + 6 - 2 * j)) & 1u) b = 0.f;
     }
     __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
     uint32_t h = *reinterpret_cast<uint32_t*>(&h2);
@@ -104,6 +114,7 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
     }
     ph[j] = h;
   }
+  if (MODE == 0 && BITS) bits |= b8 << base;
   oh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
   ol = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
@@ -304,7 +315,7 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t dsrc = (stg ? R1 : R0) + lane_sel + 32 * half;
         const float* sb = sbias + stg * 256 + 32 * half;
-        const long long mrow = m * (a.nh >> 5) + half * a.nchunk;
+        const long long mrow = m * (a.nh >> 5) + half;  // word 2c + half = channels 64c + 32half .. +31
         const uint32_t* mk = (stg ? a.mask2 : a.mask1) + mrow;
         uint32_t* bo = (stg ? a.bits2 : a.bits1) + mrow;
         const bool wait_store = a.store && (tl > 0 || stg > 0);
@@ -320,7 +331,7 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         uint32_t rA[32], rB[32];
         uint32_t mA = 0, mB = 0;
         auto fetch = [&](int c, uint32_t (&r)[32], uint32_t& mm) {
-          if (a.mode == 1) mm = live ? __ldg(mk + c) : 0u;
+          if (a.mode == 1) mm = live ? __ldg(mk + 2 * c) : 0u;
           tmem_ld32(dsrc + 64 * c, r);
         };
         auto emit = [&](int c, const uint32_t (&r)[32], const uint32_t mm) {
@@ -331,16 +342,16 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           for (int g = 0; g < 4; ++g) {
             uint4 oh, ol;
             if (a.mode == 0) {
-              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
-              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
+              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
             } else {
-              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, 8 * g, bits, oh, ol);
+              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, g, bits, oh, ol);
             }
             const uint32_t off = (uint32_t)(((half * 4 + g) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst + off) = oh;
             if (NT == 3) *reinterpret_cast<uint4*>(dst + kPlane + off) = ol;
           }
-          if (a.mode == 0 && a.store && live) bo[c] = bits;
+          if (a.mode == 0 && a.store && live) bo[2 * c] = bits;
           fence_proxy_async();  // generic-proxy writes -> visible to the MMA / TMA (async proxy)
           tc_fence_before();
           __syncwarp();
@@ -661,7 +672,7 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t reg = (stg ? R1 : R0) + lane_sel + 32 * half;
         const float* sb = sbias + stg * 256 + 32 * half;
-        const long long mrow = m * (a.nh >> 5) + half * a.nchunk;
+        const long long mrow = m * (a.nh >> 5) + half;  // word 2c + half = channels 64c + 32half .. +31
         const uint32_t* mk = (stg ? a.mask2 : a.mask1) + mrow;
         uint32_t* bo = (stg ? a.bits2 : a.bits1) + mrow;
         mbar_wait(dfull + stg, tl & 1);
@@ -674,7 +685,7 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         uint32_t rA[32], rB[32];
         uint32_t mA = 0, mB = 0;
         auto fetch = [&](int c, uint32_t (&r)[32], uint32_t& mm) {
-          if (a.mode == 1) mm = (live && !(a.exp & 2)) ? __ldg(mk + c) : 0u;
+          if (a.mode == 1) mm = (live && !(a.exp & 2)) ? __ldg(mk + 2 * c) : 0u;
           tmem_ld32(reg + 64 * c, r);
         };
         auto emit = [&](int c, const uint32_t (&r)[32], const uint32_t mm) {
@@ -684,10 +695,10 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           for (int g = 0; g < 4; ++g) {
             uint4 oh, ol;
             if (a.mode == 0) {
-              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
-              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, 8 * g, bits, oh, ol);
+              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
+              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
             } else {
-              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, 8 * g, bits, oh, ol);
+              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, g, bits, oh, ol);
             }
             wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
             wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
@@ -695,7 +706,7 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           // in place: the 32 fp32 columns just read become 16 packed hi + 16 packed lo columns
           tmem_st16(reg + 64 * c, wh);
           if (NT == 3) tmem_st16(reg + 64 * c + 16, wl);
-          if (a.mode == 0 && a.store && live) bo[c] = bits;
+          if (a.mode == 0 && a.store && live) bo[2 * c] = bits;
           if (a.store) {
             const int slot = c & 1;
             uint32_t& use = slot ? use1 : use0;
@@ -807,6 +818,490 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------- chain on CTA pairs (cta_group::2)
+// k_rb_chain_t is bound by shared-memory bandwidth, not by the tensor pipe: an M = 128 MMA reads 64 B/clk of its B
+// operand while TMA writes the next weight stage (42 B/clk) against a 128 B/clk port, so every MMA runs ~1.35x
+// (GEMM2) to 2x (GEMM1 / GEMM3) over its floor (chain_trace.py; skipping the weight loads altogether changes
+// nothing, so it is not L2).  k_rb_chain2 runs the same pipeline on a CLUSTER OF TWO CTAs: each CTA owns one
+// 128-pixel tile (its own TMEM, epilogue and stores), the leader CTA issues tcgen05.mma.cta_group::2 with
+// M = 256 over both tiles, and each CTA holds only HALF of every weight stage (N/2 rows).  B reads and TMA
+// writes per SM halve (32 + 21 B/clk).  The epilogue is spread over 16 warps (16 channels x 32 rows per chunk
+// each, i.e. one k-step of the next GEMM per warp) so that it keeps up with the faster MMAs.
+//
+// Cross-CTA protocol: weight / im2col stages - both CTAs' TMA loads complete_tx on the LEADER's full barrier
+// (cp.async.bulk.tensor ... cta_group::2), the leader's producer posts the expect_tx for both; stage release and
+// accumulator-ready signals are tcgen05.commit.cta_group::2 multicast to both CTAs; "hidden operand ready" is
+// counted on the leader's barrier by the epilogue warps of both CTAs (remote mbarrier.arrive).
+// Warps: 0 TMA producer | 1 MMA issuer (leader only) | 2..17 epilogue | 18 TMA store of the hidden tensors.
+constexpr int kEpi2Warps = 16;
+constexpr int kChain2Threads = 32 * (2 + kEpi2Warps + 1);
+constexpr int kChain2Slots = 3;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta) as for a local arrive: what the leader's MMA consumes lives in tensor memory and is
+  // ordered by tcgen05.wait::st + tcgen05.fence::before_thread_sync; a .release.cluster here costs ~1000 cycles per arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// TMA load into THIS CTA's shared memory whose completion is counted on a barrier given as a shared::cluster
+// address (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(const void* tmap, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <int NT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChain2Threads, 1)
+k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
+  constexpr int NP = (NT == 1) ? 1 : 2;
+  constexpr uint32_t STAGE = NP * kPlane;  // one ring stage: [<= 128 rows][64 k] per plane (per CTA)
+  constexpr uint32_t SLOT = 2 * kPlane;    // one staging slot: hi + lo planes of a 128 x 64 chunk
+  constexpr int EPI = kEpi2Warps * 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stag = smem;
+  uint8_t* ring = stag + kChain2Slots * SLOT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * STAGE);
+  uint64_t* empty = full + 8;
+  uint64_t* dfull = empty + 8;    // [3]
+  uint64_t* hready = dfull + 3;   // [4]  (leader's copy is the live one)
+  uint64_t* sready = hready + 4;  // [3]
+  uint64_t* sfree = sready + 3;   // [3]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sfree + 3 + 3);  // 32 barrier slots -> 256 bytes
+  float* sbias = reinterpret_cast<float*>(tslot + 4);            // [2][256]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int npairs = (a.ntiles + 1) >> 1;
+  const int pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
+  const int nhalf = a.nh >> 1;        // weight rows of GEMM1 / GEMM2 held by this CTA
+  const int n3half = a.n3pad >> 1;    // weight rows of GEMM3 held by this CTA
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    prefetch_tmap(&maps.A[0]);
+    prefetch_tmap(&maps.W1[0]);
+    prefetch_tmap(&maps.W2[0]);
+    prefetch_tmap(&maps.W3[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+      for (int s = 0; s < 3; ++s) mbar_init(dfull + s, 1);
+      for (int s = 0; s < 4; ++s) mbar_init(hready + s, 2 * kEpi2Warps);
+      for (int s = 0; s < kChain2Slots; ++s) { mbar_init(sready + s, kEpi2Warps); mbar_init(sfree + s, 1); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc2(tslot, 512);
+    tmem_relinquish2();
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const float* bp = (i < 256) ? a.bias1 : a.bias2;
+    const int j = i & 255;
+    sbias[i] = (bp && j < a.nh) ? bp[j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised and its tensor memory is allocated
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      uint32_t it = 0;
+      // wait for the local stage to be free, (leader) post the bytes of BOTH CTAs, return the stage and the
+      // leader's full barrier
+      auto acquire = [&](uint32_t bytes_per_cta, uint32_t& bar) -> uint8_t* {
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        if (leader) mbar_expect_tx(full + s, 2 * bytes_per_cta);
+        bar = mapa_u32(smem_u32(full + s), 0);
+        ++it;
+        return ring + (size_t)s * STAGE;
+      };
+      for (int tp = pair0; tp < npairs; tp += pstride) {
+        const int tile = 2 * tp + (int)rank;
+        uint32_t bar;
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          uint8_t* st = acquire(NP * kPlane, bar);  // 128 pixels x 64 im2col columns of this CTA's tile
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.A[pl], bar, st + pl * kPlane, kb * 64, tile * 128);
+          st = acquire(NP * nhalf * 128, bar);
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W1[pl], bar, st + pl * kPlane, kb * 64, (int)rank * nhalf);
+        }
+        for (int c = 0; c < a.nchunk; ++c) {
+          uint8_t* st = acquire(NP * nhalf * 128, bar);
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * kPlane, c * 64, (int)rank * nhalf);
+        }
+        for (int c = 0; c < a.nchunk; ++c) {
+          uint8_t* st = acquire(NP * n3half * 128, bar);
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W3[pl], bar, st + pl * kPlane, c * 64, (int)rank * n3half);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, both tiles of the pair)
+    if (leader && elect_one()) {
+      const uint32_t idesc_12 = make_idesc_bf16(256, a.nh, 0, 0);
+      const uint32_t idesc_3 = make_idesc_bf16(256, a.n3pad, 0, 0);
+      const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
+      uint32_t it = 0, tl = 0;
+      long long twait = 0;
+      auto stage_wait = [&]() -> uint32_t {
+        const int s = it % a.stages;
+        const uint32_t ph = (it / a.stages) & 1;
+        const long long t0 = a.trace ? clock64() : 0;
+        mbar_wait_cluster(full + s, ph);
+        if (a.trace) twait += clock64() - t0;
+        tc_fence_after();
+        return smem_u32(ring + (size_t)s * STAGE);
+      };
+      auto mma_block_ss = [&](uint32_t d_tmem, uint32_t idesc, uint32_t a_addr, uint32_t b_addr, uint32_t first) {
+        const uint32_t alo = (a_addr >> 4) & 0x3FFF, blo = (b_addr >> 4) & 0x3FFF;
+#pragma unroll
+        for (int term = 0; term < NT; ++term) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ((uint64_t)dhi << 32) | (alo + ((term == 2) ? (kPlane >> 4) : 0) + 2 * k);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            umma2_f16(d_tmem, ad, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
+          }
+        }
+      };
+      // A = chunk c of the hidden operand in tensor memory: k-step k at column ra + 64c + 16k (hi), + 8 (lo)
+      auto mma_block_ts = [&](uint32_t d_tmem, uint32_t idesc, uint32_t ra, int c, uint32_t b_addr, uint32_t first) {
+        const uint32_t blo = (b_addr >> 4) & 0x3FFF;
+#pragma unroll
+        for (int term = 0; term < NT; ++term) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t at = ra + 64 * c + 16 * k + ((term == 2) ? 8 : 0);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            umma2_f16_ts(d_tmem, at, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
+          }
+        }
+      };
+      for (int tp = pair0; tp < npairs; tp += pstride, ++tl) {
+        const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
+        long long* tr = (a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
+        if (tr) tr[0] = clock64();
+        if (tl > 0) {  // R0 held the A operand of the previous pair's GEMM3: let those MMAs retire first
+          mbar_wait(dfull + 2, (tl - 1) & 1);
+          tc_fence_after();
+        }
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+          const uint32_t sA = stage_wait();
+          const int slotA = it % a.stages;
+          ++it;
+          const uint32_t sb = stage_wait();
+          mma_block_ss(R0, idesc_12, sA, sb, kb == 0);
+          umma2_commit_mc(empty + it % a.stages);
+          ++it;
+          umma2_commit_mc(empty + slotA);
+        }
+        umma2_commit_mc(dfull + 0);
+        if (tr) { tr[1] = clock64(); tr[12] = twait; }
+        twait = 0;
+        for (int c = 0; c < a.nchunk; ++c, ++it) {
+          mbar_wait_cluster(hready + c, 0);
+          tc_fence_after();
+          if (tr && c == 0) tr[2] = clock64();
+          const uint32_t sb = stage_wait();
+          mma_block_ts(R1, idesc_12, R0, c, sb, c == 0);
+          umma2_commit_mc(empty + it % a.stages);
+        }
+        umma2_commit_mc(dfull + 1);
+        if (tr) { tr[3] = clock64(); tr[13] = twait; }
+        twait = 0;
+        for (int c = 0; c < a.nchunk; ++c, ++it) {
+          mbar_wait_cluster(hready + c, 1);
+          tc_fence_after();
+          if (tr && c == 0) tr[4] = clock64();
+          const uint32_t sb = stage_wait();
+          mma_block_ts(R0, idesc_3, R1, c, sb, c == 0);
+          umma2_commit_mc(empty + it % a.stages);
+        }
+        umma2_commit_mc(dfull + 2);
+        if (tr) { tr[5] = clock64(); tr[14] = twait; }
+        twait = 0;
+      }
+    }
+  } else if (warp < 2 + kEpi2Warps) {
+    // ------------------------------------------------------------ epilogue warps (both CTAs, own tile)
+    const int e = warp - 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
+    const int kk = e >> 2;    // which 16 channels of a 64-channel chunk (= k-step of the next GEMM)
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int tid = e * 32 + lane;
+    const uint32_t hready_leader = mapa_u32(smem_u32(hready), 0);
+    uint32_t tl = 0;
+    uint32_t cs = 0;  // chunk stores issued so far (store mode): slot cs % 3, use cs / 3
+    for (int tp = pair0; tp < npairs; tp += pstride, ++tl) {
+      const int tile = 2 * tp + (int)rank;
+      const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
+      const long long m = (long long)tile * 128 + row;
+      const bool live = m < a.M;
+      long long* tr = (a.trace && blockIdx.x == 0 && tl < 16 && e == 0 && lane == 0) ? a.trace + tl * 16 + 6 : nullptr;
+#pragma unroll 1
+      for (int stg = 0; stg < 2; ++stg) {
+        const uint32_t reg = (stg ? R1 : R0) + lane_sel + 16 * kk;
+        const float* sb = sbias + stg * 256 + 16 * kk;
+        const long long hrow = m * (a.nh >> 4) + kk;  // 16-bit word 4c + kk of the row's bit plane
+        const uint16_t* mk = reinterpret_cast<const uint16_t*>(stg ? a.mask2 : a.mask1) + hrow;
+        uint16_t* bo = reinterpret_cast<uint16_t*>(stg ? a.bits2 : a.bits1) + hrow;
+        uint32_t mA = 0, mB = 0;
+        if (a.mode == 1) mA = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk) : 0u;  // chunk 0's mask, before the wait
+        mbar_wait(dfull + stg, tl & 1);
+        tc_fence_after();
+        if (stg == 0 && tl > 0) {  // the P stores of the previous tile have read the staging area
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        }
+        if (tr) tr[2 * stg] = clock64();
+        uint32_t rA[16], rB[16];
+        auto fetch = [&](int c, uint32_t (&r)[16], uint32_t& mm) {
+          if (a.mode == 1 && c > 0) mm = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk + 4 * c) : 0u;
+          tmem_ld16(reg + 64 * c, r);
+        };
+        auto emit = [&](int c, const uint32_t (&r)[16], const uint32_t mm) {
+          uint32_t wh[8], wl[8];
+          uint32_t bits = 0;
+          // fine-grained timeline of one warp (third tile of CTA 0): rows 16.. of the trace block, one row per chunk
+          long long* tq = (a.trace && blockIdx.x == 0 && tl == 2 && e == 0 && lane == 0) ? a.trace + 256 + (stg * 4 + c) * 16 : nullptr;
+          if (tq) tq[0] = clock64();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 oh, ol;
+            if (a.mode == 0) {
+              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
+              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
+            } else {
+              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, g, bits, oh, ol);
+            }
+            wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
+            wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
+          }
+          if (tq) tq[1] = clock64();
+          // in place: the 16 fp32 columns just read become 8 packed hi + 8 packed lo columns
+          tmem_st8(reg + 64 * c, wh);
+          if (NT == 3) tmem_st8(reg + 64 * c + 8, wl);
+          if (a.mode == 0 && a.store && live) bo[4 * c] = (uint16_t)bits;
+          int slot = 0;
+          if (a.store) {
+            slot = (int)(cs % kChain2Slots);
+            const uint32_t use = cs / kChain2Slots;
+            if (tq) tq[2] = clock64();
+            if (use > 0) mbar_wait(sfree + slot, (use - 1) & 1);  // the slot's previous TMA store has read it
+            if (tq) tq[3] = clock64();
+            uint8_t* dst = stag + slot * SLOT + row * 128;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t off = (uint32_t)(((kk * 2 + g) ^ (row & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst + off) = make_uint4(wh[4 * g], wh[4 * g + 1], wh[4 * g + 2], wh[4 * g + 3]);
+              if (NT == 3)
+                *reinterpret_cast<uint4*>(dst + kPlane + off) = make_uint4(wl[4 * g], wl[4 * g + 1], wl[4 * g + 2], wl[4 * g + 3]);
+            }
+            fence_proxy_async();
+            ++cs;
+          }
+          if (tq) tq[4] = clock64();
+          tmem_st_wait();
+          if (tq) tq[5] = clock64();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_cluster(hready_leader + 8 * c);
+            if (a.store) mbar_arrive(sready + slot);
+          }
+          if (tq) tq[6] = clock64();
+        };
+        fetch(0, rA, mA);
+#pragma unroll 1
+        for (int c = 0; c < a.nchunk; c += 2) {
+          long long* tq = (a.trace && blockIdx.x == 0 && tl == 2 && e == 0 && lane == 0) ? a.trace + 256 + (stg * 4 + c) * 16 : nullptr;
+          if (tq) tq[7] = clock64();
+          tmem_ld_wait();
+          if (tq) tq[8] = clock64();
+          fetch(c + 1, rB, mB);
+          emit(c, rA, mA);
+          if (tq) tq[16 + 7] = clock64();
+          tmem_ld_wait();
+          if (tq) tq[16 + 8] = clock64();
+          if (c + 2 < a.nchunk) fetch(c + 2, rA, mA);
+          emit(c + 1, rB, mB);
+        }
+        if (tr) tr[2 * stg + 1] = clock64();
+      }
+      // E3: tap-expanded columns (region R0, <= 256 of them) -> staging -> TMA store of P
+      mbar_wait(dfull + 2, tl & 1);
+      tc_fence_after();
+      if (tr) tr[4] = clock64();
+      if (a.store) {  // every staging slot: its last TMA store has read it
+#pragma unroll
+        for (int sl = 0; sl < kChain2Slots; ++sl) {
+          const uint32_t uses = (cs + kChain2Slots - 1 - sl) / kChain2Slots;
+          if (uses > 0) mbar_wait(sfree + sl, (uses - 1) & 1);
+        }
+      }
+#pragma unroll 1
+      for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
+        const int ncols = min(128, a.n3pad - slab * 128);
+        const uint32_t dsrc = R0 + slab * 128 + lane_sel;
+        if (slab > 0) {
+          if (tid == 0) bulk_wait_read0();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        }
+        // warp group kk stages the 32-column group kk of the slab (the TMA store's SWIZZLE_128B box layout)
+        auto stage16 = [&](int col, const uint32_t* r) {
+          uint8_t* g = stag + (col >> 5) * kPlane + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = ((col & 31) >> 2) + j;
+            *reinterpret_cast<uint4*>(g + ((ch ^ (row & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        };
+        const int c0 = 32 * kk;
+        if (c0 + 32 <= ncols) {
+          uint32_t r[32];
+          tmem_ld32(dsrc + c0, r);
+          tmem_ld_wait();
+          stage16(c0, r);
+          stage16(c0 + 16, r + 16);
+        } else if (c0 < ncols) {
+          uint32_t r[16];
+          tmem_ld16(dsrc + c0, r);
+          tmem_ld_wait();
+          stage16(c0, r);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        if (tid == 0) {
+          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, stag + g * kPlane, slab * 128 + g * 32, tile * 128);
+          bulk_commit();
+        }
+      }
+      if (tr) tr[5] = clock64();
+    }
+    if (tid == 0) bulk_wait0();
+  } else if (a.store) {
+    // ------------------------------------------------------------ TMA store warp: hidden chunks -> HBM
+    if (lane == 0) {
+      uint32_t cs = 0;
+      int prev = -1;  // slot of a committed store whose shared-memory read has not been acknowledged yet
+      for (int tp = pair0; tp < npairs; tp += pstride) {
+        const int tile = 2 * tp + (int)rank;
+        for (int stg = 0; stg < 2; ++stg) {
+          for (int c = 0; c < a.nchunk; ++c, ++cs) {
+            const int slot = (int)(cs % kChain2Slots);
+            mbar_wait(sready + slot, (cs / kChain2Slots) & 1);
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl)
+              tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+            bulk_commit();
+            if (stg == 1 && c == a.nchunk - 1) {
+              // last chunk of the tile: E3 reuses the staging area, so everything is acknowledged now
+              bulk_wait_read0();
+              if (prev >= 0) mbar_arrive(sfree + prev);
+              mbar_arrive(sfree + slot);
+              prev = -1;
+            } else {
+              if (prev >= 0) {  // one store stays in flight; the one before it has read its slot
+                bulk_wait_read1();
+                mbar_arrive(sfree + prev);
+              }
+              prev = slot;
+            }
+          }
+        }
+      }
+      bulk_wait0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer may still signal or read it
+  if (warp == 1) tmem_dealloc2(tmem, 512);
 }
 
 // ---------------------------------------------------------------- col2im
@@ -994,22 +1489,30 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
   const size_t aux = 32 * 8 + 16 + 512 * 4;
   const size_t cap = 227 * 1024;
-  // hidden operand in tensor memory (k_rb_chain_t) unless GEMM3 needs more than one 256-column region
-  static const bool force_smem = [] { const char* e = getenv("INB_CHAIN_SMEM"); return e && e[0] == '1'; }();
-  const bool tmem_a = a.n3pad <= 256 && !force_smem;
-  const size_t fixed = tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk;
+  // kernel choice: CTA pairs (k_rb_chain2) whenever GEMM3 fits one 256-column region; INB_CHAIN_KERNEL=t|smem forces
+  // the single-CTA kernels (hidden operand in tensor memory / in shared memory)
+  static const int force = [] {
+    const char* e = getenv("INB_CHAIN_KERNEL");
+    if (!e) e = getenv("INB_CHAIN_SMEM") && getenv("INB_CHAIN_SMEM")[0] == '1' ? "smem" : "";
+    return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
+  }();
+  const bool pair = a.n3pad <= 256 && force == 0;
+  const bool tmem_a = a.n3pad <= 256 && force != 2;
+  const size_t fixed = pair ? (size_t)kChain2Slots * 2 * kPlane : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
   int stages = (int)((cap - aux - fixed) / stage);
   if (stages > 8) stages = 8;
-  // the im2col block of GEMM1 stays resident while the nh/128 weight halves stream past it
-  INB_CHECK(stages >= 1 + s.nh / 128, "fused ResidualBlock chain: shared memory does not fit");
+  if (pair && stages > 4) stages = 4;
+  // the im2col block of GEMM1 stays resident while the weight blocks stream past it
+  INB_CHECK(stages >= (pair ? 2 : 1 + s.nh / 128), "fused ResidualBlock chain: shared memory does not fit");
   a.stages = stages;
   const size_t smem = fixed + stages * stage + aux;
   ChainMaps mp{};
+  const int wrows = pair ? s.nh / 2 : 128, w3rows = pair ? a.n3pad / 2 : 128;
   for (int pl = 0; pl < 2; ++pl) {
     mp.A[pl] = make_rows_map(pl ? s.in.lo : s.in.hi, s.in.pitch, a.M, 64, 128);
-    mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, 128);
-    mp.W2[pl] = make_rows_map(pl ? s.w2.lo : s.w2.hi, s.nh, s.nh, 64, 128);
-    mp.W3[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 64, 128);
+    mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, wrows);
+    mp.W2[pl] = make_rows_map(pl ? s.w2.lo : s.w2.hi, s.nh, s.nh, 64, wrows);
+    mp.W3[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 64, w3rows);
     if (a.store) {
       mp.O1[pl] = make_rows_map(pl ? s.o1.lo : s.o1.hi, s.nh, a.M, 64, 128);
       mp.O2[pl] = make_rows_map(pl ? s.o2.lo : s.o2.hi, s.nh, a.M, 64, 128);
@@ -1019,11 +1522,33 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     }
   }
   mp.P = make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
-  const unsigned grid = (unsigned)std::min(a.ntiles, 148);
+  unsigned grid = (unsigned)std::min(a.ntiles, 148);
   const double flops = 2.0 * a.M * ((double)s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
   {
     Prof pf(c, F_CONV_TC, 1, flops, 0);
-    if (tmem_a && NT == 3) {
+    if (pair) {
+      auto kern = (NT == 3) ? k_rb_chain2<3> : k_rb_chain2<1>;
+      INB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // resident CTA pairs: one CTA per SM, pairs are placed inside a GPC (the query accounts for odd GPCs)
+      static int max_pairs[2] = {0, 0};
+      int& mpairs = max_pairs[NT == 3];
+      if (mpairs == 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(148);
+        cfg.blockDim = dim3(kChain2Threads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 64; }
+        mpairs = std::min(n, 74);
+      }
+      grid = 2u * (unsigned)std::min((a.ntiles + 1) / 2, mpairs);
+      kern<<<grid, kChain2Threads, smem, c.st>>>(mp, a);
+    } else if (tmem_a && NT == 3) {
       INB_CUDA(cudaFuncSetAttribute(k_rb_chain_t<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_rb_chain_t<3><<<grid, kChainThreads, smem, c.st>>>(mp, a);
     } else if (tmem_a) {
