@@ -837,7 +837,7 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
 // Warps: 0 TMA producer | 1 MMA issuer (leader only) | 2..17 epilogue | 18 TMA store of the hidden tensors.
 constexpr int kEpi2Warps = 16;
 constexpr int kChain2Threads = 32 * (2 + kEpi2Warps + 1);
-constexpr int kChain2Slots = 3;
+constexpr int kChain2Slots = 2;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -931,24 +931,30 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr uint32_t STAGE = NP * kPlane;  // one ring stage: [<= 128 rows][64 k] per plane (per CTA)
   constexpr uint32_t SLOT = 2 * kPlane;    // one staging slot: hi + lo planes of a 128 x 64 chunk
   constexpr int EPI = kEpi2Warps * 32;
+  // shared memory: [2 staging slots of the hidden-tensor stores][P slab staging 64 KB][ring][barriers, biases]
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stag = smem;
-  uint8_t* ring = stag + kChain2Slots * SLOT;
+  uint8_t* pstag = stag + kChain2Slots * SLOT;
+  uint8_t* ring = pstag + 4 * kPlane;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * STAGE);
   uint64_t* empty = full + 8;
-  uint64_t* dfull = empty + 8;    // [3]
-  uint64_t* hready = dfull + 3;   // [4]  (leader's copy is the live one)
-  uint64_t* sready = hready + 4;  // [3]
-  uint64_t* sfree = sready + 3;   // [3]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(sfree + 3 + 3);  // 32 barrier slots -> 256 bytes
-  float* sbias = reinterpret_cast<float*>(tslot + 4);            // [2][256]
+  uint64_t* d1h = empty + 8;      // [2]  column half h of D1 is complete
+  uint64_t* d2h = d1h + 2;        // [2]  column half h of D2 is complete
+  uint64_t* d3f = d2h + 2;        // [1]
+  uint64_t* hready = d3f + 1;     // [4]  (leader's copy is the live one)
+  uint64_t* sready = hready + 4;  // [2]
+  uint64_t* sfree = sready + 2;   // [2]
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 32);  // 32 barrier slots -> 256 bytes
+  float* sbias = reinterpret_cast<float*>(tslot + 4);        // [2][256]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int npairs = (a.ntiles + 1) >> 1;
   const int pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
-  const int nhalf = a.nh >> 1;        // weight rows of GEMM1 / GEMM2 held by this CTA
+  const int nhh = a.nh >> 1;          // columns of one half of D1 / D2
+  const int qrows = a.nh >> 2;        // weight rows of one half held by this CTA
   const int n3half = a.n3pad >> 1;    // weight rows of GEMM3 held by this CTA
+  const int chalf = a.nchunk >> 1;    // chunks per column half
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -960,7 +966,8 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-      for (int s = 0; s < 3; ++s) mbar_init(dfull + s, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(d1h + s, 1); mbar_init(d2h + s, 1); }
+      mbar_init(d3f, 1);
       for (int s = 0; s < 4; ++s) mbar_init(hready + s, 2 * kEpi2Warps);
       for (int s = 0; s < kChain2Slots; ++s) { mbar_init(sready + s, kEpi2Warps); mbar_init(sfree + s, 1); }
       fence_barrier_init();
@@ -1002,14 +1009,20 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           uint8_t* st = acquire(NP * kPlane, bar);  // 128 pixels x 64 im2col columns of this CTA's tile
 #pragma unroll
           for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.A[pl], bar, st + pl * kPlane, kb * 64, tile * 128);
-          st = acquire(NP * nhalf * 128, bar);
+          for (int h = 0; h < 2; ++h) {
+            st = acquire(NP * qrows * 128, bar);
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W1[pl], bar, st + pl * kPlane, kb * 64, (int)rank * nhalf);
+            for (int pl = 0; pl < NP; ++pl)
+              tma_load_2d_cg2(&maps.W1[pl], bar, st + pl * kPlane, kb * 64, h * nhh + (int)rank * qrows);
+          }
         }
-        for (int c = 0; c < a.nchunk; ++c) {
-          uint8_t* st = acquire(NP * nhalf * 128, bar);
+        for (int h = 0; h < 2; ++h) {
+          for (int c = 0; c < a.nchunk; ++c) {
+            uint8_t* st = acquire(NP * qrows * 128, bar);
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * kPlane, c * 64, (int)rank * nhalf);
+            for (int pl = 0; pl < NP; ++pl)
+              tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * kPlane, c * 64, h * nhh + (int)rank * qrows);
+          }
         }
         for (int c = 0; c < a.nchunk; ++c) {
           uint8_t* st = acquire(NP * n3half * 128, bar);
@@ -1021,7 +1034,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, both tiles of the pair)
     if (leader && elect_one()) {
-      const uint32_t idesc_12 = make_idesc_bf16(256, a.nh, 0, 0);
+      const uint32_t idesc_12 = make_idesc_bf16(256, nhh, 0, 0);   // GEMM1 / GEMM2 run one column half at a time
       const uint32_t idesc_3 = make_idesc_bf16(256, a.n3pad, 0, 0);
       const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
       uint32_t it = 0, tl = 0;
@@ -1065,31 +1078,38 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         long long* tr = (a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
         if (tr) tr[0] = clock64();
         if (tl > 0) {  // R0 held the A operand of the previous pair's GEMM3: let those MMAs retire first
-          mbar_wait(dfull + 2, (tl - 1) & 1);
+          mbar_wait(d3f, (tl - 1) & 1);
           tc_fence_after();
         }
+        // GEMM1: both column halves per im2col block (the block stays resident while its two weight halves pass)
         for (int kb = 0; kb < a.nkb1; ++kb) {
           const uint32_t sA = stage_wait();
           const int slotA = it % a.stages;
           ++it;
-          const uint32_t sb = stage_wait();
-          mma_block_ss(R0, idesc_12, sA, sb, kb == 0);
-          umma2_commit_mc(empty + it % a.stages);
-          ++it;
+          for (int h = 0; h < 2; ++h, ++it) {
+            const uint32_t sb = stage_wait();
+            mma_block_ss(R0 + h * nhh, idesc_12, sA, sb, kb == 0);
+            umma2_commit_mc(empty + it % a.stages);
+            if (kb == a.nkb1 - 1) umma2_commit_mc(d1h + h);
+          }
           umma2_commit_mc(empty + slotA);
         }
-        umma2_commit_mc(dfull + 0);
         if (tr) { tr[1] = clock64(); tr[12] = twait; }
         twait = 0;
-        for (int c = 0; c < a.nchunk; ++c, ++it) {
-          mbar_wait_cluster(hready + c, 0);
-          tc_fence_after();
-          if (tr && c == 0) tr[2] = clock64();
-          const uint32_t sb = stage_wait();
-          mma_block_ts(R1, idesc_12, R0, c, sb, c == 0);
-          umma2_commit_mc(empty + it % a.stages);
+        // GEMM2: column half 0 over all chunks (paced by E1), then half 1 (its epilogue E2 of half 0 runs under it)
+        for (int h = 0; h < 2; ++h) {
+          for (int c = 0; c < a.nchunk; ++c, ++it) {
+            if (h == 0) {
+              mbar_wait_cluster(hready + c, 0);
+              tc_fence_after();
+              if (tr && c == 0) tr[2] = clock64();
+            }
+            const uint32_t sb = stage_wait();
+            mma_block_ts(R1 + h * nhh, idesc_12, R0, c, sb, c == 0);
+            umma2_commit_mc(empty + it % a.stages);
+          }
+          umma2_commit_mc(d2h + h);
         }
-        umma2_commit_mc(dfull + 1);
         if (tr) { tr[3] = clock64(); tr[13] = twait; }
         twait = 0;
         for (int c = 0; c < a.nchunk; ++c, ++it) {
@@ -1100,7 +1120,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           mma_block_ts(R0, idesc_3, R1, c, sb, c == 0);
           umma2_commit_mc(empty + it % a.stages);
         }
-        umma2_commit_mc(dfull + 2);
+        umma2_commit_mc(d3f);
         if (tr) { tr[5] = clock64(); tr[14] = twait; }
         twait = 0;
       }
@@ -1115,7 +1135,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     const int tid = e * 32 + lane;
     const uint32_t hready_leader = mapa_u32(smem_u32(hready), 0);
     uint32_t tl = 0;
-    uint32_t cs = 0;  // chunk stores issued so far (store mode): slot cs % 3, use cs / 3
+    uint32_t cs = 0;  // chunk stores issued so far (store mode): slot cs % 2, use cs / 2
     for (int tp = pair0; tp < npairs; tp += pstride, ++tl) {
       const int tile = 2 * tp + (int)rank;
       const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
@@ -1129,26 +1149,24 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         const long long hrow = m * (a.nh >> 4) + kk;  // 16-bit word 4c + kk of the row's bit plane
         const uint16_t* mk = reinterpret_cast<const uint16_t*>(stg ? a.mask2 : a.mask1) + hrow;
         uint16_t* bo = reinterpret_cast<uint16_t*>(stg ? a.bits2 : a.bits1) + hrow;
+        uint64_t* dh = stg ? d2h : d1h;
         uint32_t mA = 0, mB = 0;
         if (a.mode == 1) mA = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk) : 0u;  // chunk 0's mask, before the wait
-        mbar_wait(dfull + stg, tl & 1);
+        mbar_wait(dh + 0, tl & 1);
         tc_fence_after();
-        if (stg == 0 && tl > 0) {  // the P stores of the previous tile have read the staging area
-          if (tid == 0) bulk_wait_read0();
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
-        }
         if (tr) tr[2 * stg] = clock64();
         uint32_t rA[16], rB[16];
         auto fetch = [&](int c, uint32_t (&r)[16], uint32_t& mm) {
+          if (c == chalf) {  // first chunk of the second column half
+            mbar_wait(dh + 1, tl & 1);
+            tc_fence_after();
+          }
           if (a.mode == 1 && c > 0) mm = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk + 4 * c) : 0u;
           tmem_ld16(reg + 64 * c, r);
         };
         auto emit = [&](int c, const uint32_t (&r)[16], const uint32_t mm) {
           uint32_t wh[8], wl[8];
           uint32_t bits = 0;
-          // fine-grained timeline of one warp (third tile of CTA 0): rows 16.. of the trace block, one row per chunk
-          long long* tq = (a.trace && blockIdx.x == 0 && tl == 2 && e == 0 && lane == 0) ? a.trace + 256 + (stg * 4 + c) * 16 : nullptr;
-          if (tq) tq[0] = clock64();
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint4 oh, ol;
@@ -1161,7 +1179,6 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
             wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
           }
-          if (tq) tq[1] = clock64();
           // in place: the 16 fp32 columns just read become 8 packed hi + 8 packed lo columns
           tmem_st8(reg + 64 * c, wh);
           if (NT == 3) tmem_st8(reg + 64 * c + 8, wl);
@@ -1170,9 +1187,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           if (a.store) {
             slot = (int)(cs % kChain2Slots);
             const uint32_t use = cs / kChain2Slots;
-            if (tq) tq[2] = clock64();
             if (use > 0) mbar_wait(sfree + slot, (use - 1) & 1);  // the slot's previous TMA store has read it
-            if (tq) tq[3] = clock64();
             uint8_t* dst = stag + slot * SLOT + row * 128;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -1184,56 +1199,47 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             fence_proxy_async();
             ++cs;
           }
-          if (tq) tq[4] = clock64();
           tmem_st_wait();
-          if (tq) tq[5] = clock64();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive_cluster(hready_leader + 8 * c);
             if (a.store) mbar_arrive(sready + slot);
           }
-          if (tq) tq[6] = clock64();
         };
         fetch(0, rA, mA);
 #pragma unroll 1
         for (int c = 0; c < a.nchunk; c += 2) {
-          long long* tq = (a.trace && blockIdx.x == 0 && tl == 2 && e == 0 && lane == 0) ? a.trace + 256 + (stg * 4 + c) * 16 : nullptr;
-          if (tq) tq[7] = clock64();
+          // the next chunk's TMEM load is issued before this chunk is converted - unless it belongs to the second
+          // column half, whose completion must not hold up the hand-over of this chunk
           tmem_ld_wait();
-          if (tq) tq[8] = clock64();
-          fetch(c + 1, rB, mB);
+          const bool late1 = (c + 1 == chalf);
+          if (!late1) fetch(c + 1, rB, mB);
           emit(c, rA, mA);
-          if (tq) tq[16 + 7] = clock64();
+          if (late1) fetch(c + 1, rB, mB);
           tmem_ld_wait();
-          if (tq) tq[16 + 8] = clock64();
-          if (c + 2 < a.nchunk) fetch(c + 2, rA, mA);
+          const bool more = c + 2 < a.nchunk, late2 = (c + 2 == chalf);
+          if (more && !late2) fetch(c + 2, rA, mA);
           emit(c + 1, rB, mB);
+          if (more && late2) fetch(c + 2, rA, mA);
         }
         if (tr) tr[2 * stg + 1] = clock64();
       }
-      // E3: tap-expanded columns (region R0, <= 256 of them) -> staging -> TMA store of P
-      mbar_wait(dfull + 2, tl & 1);
+      // E3: tap-expanded columns (region R0, <= 256 of them) -> P staging -> TMA store of P
+      mbar_wait(d3f, tl & 1);
       tc_fence_after();
       if (tr) tr[4] = clock64();
-      if (a.store) {  // every staging slot: its last TMA store has read it
-#pragma unroll
-        for (int sl = 0; sl < kChain2Slots; ++sl) {
-          const uint32_t uses = (cs + kChain2Slots - 1 - sl) / kChain2Slots;
-          if (uses > 0) mbar_wait(sfree + sl, (uses - 1) & 1);
-        }
-      }
 #pragma unroll 1
       for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
         const int ncols = min(128, a.n3pad - slab * 128);
         const uint32_t dsrc = R0 + slab * 128 + lane_sel;
-        if (slab > 0) {
+        if (slab > 0 || tl > 0) {  // the previous P stores have read the staging area (long ago when slab == 0)
           if (tid == 0) bulk_wait_read0();
           asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
         }
         // warp group kk stages the 32-column group kk of the slab (the TMA store's SWIZZLE_128B box layout)
         auto stage16 = [&](int col, const uint32_t* r) {
-          uint8_t* g = stag + (col >> 5) * kPlane + row * 128;
+          uint8_t* g = pstag + (col >> 5) * kPlane + row * 128;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int ch = ((col & 31) >> 2) + j;
@@ -1257,7 +1263,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
         if (tid == 0) {
-          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, stag + g * kPlane, slab * 128 + g * 32, tile * 128);
+          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, pstag + g * kPlane, slab * 128 + g * 32, tile * 128);
           bulk_commit();
         }
       }
@@ -1268,7 +1274,6 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     // ------------------------------------------------------------ TMA store warp: hidden chunks -> HBM
     if (lane == 0) {
       uint32_t cs = 0;
-      int prev = -1;  // slot of a committed store whose shared-memory read has not been acknowledged yet
       for (int tp = pair0; tp < npairs; tp += pstride) {
         const int tile = 2 * tp + (int)rank;
         for (int stg = 0; stg < 2; ++stg) {
@@ -1279,21 +1284,16 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             for (int pl = 0; pl < NP; ++pl)
               tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
             bulk_commit();
-            if (stg == 1 && c == a.nchunk - 1) {
-              // last chunk of the tile: E3 reuses the staging area, so everything is acknowledged now
-              bulk_wait_read0();
-              if (prev >= 0) mbar_arrive(sfree + prev);
-              mbar_arrive(sfree + slot);
-              prev = -1;
-            } else {
-              if (prev >= 0) {  // one store stays in flight; the one before it has read its slot
-                bulk_wait_read1();
-                mbar_arrive(sfree + prev);
-              }
-              prev = slot;
+            if (cs > 0) {  // one store stays in flight; the one before it has read its slot
+              bulk_wait_read1();
+              mbar_arrive(sfree + (int)((cs - 1) % kChain2Slots));
             }
           }
         }
+      }
+      if (cs > 0) {
+        bulk_wait_read0();
+        mbar_arrive(sfree + (int)((cs - 1) % kChain2Slots));
       }
       bulk_wait0();
     }
@@ -1498,7 +1498,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   }();
   const bool pair = a.n3pad <= 256 && force == 0;
   const bool tmem_a = a.n3pad <= 256 && force != 2;
-  const size_t fixed = pair ? (size_t)kChain2Slots * 2 * kPlane : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
+  const size_t fixed = pair ? (size_t)(kChain2Slots * 2 + 4) * kPlane : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
   int stages = (int)((cap - aux - fixed) / stage);
   if (stages > 8) stages = 8;
   if (pair && stages > 4) stages = 4;
@@ -1507,7 +1507,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.stages = stages;
   const size_t smem = fixed + stages * stage + aux;
   ChainMaps mp{};
-  const int wrows = pair ? s.nh / 2 : 128, w3rows = pair ? a.n3pad / 2 : 128;
+  const int wrows = pair ? s.nh / 4 : 128, w3rows = pair ? a.n3pad / 2 : 128;
   for (int pl = 0; pl < 2; ++pl) {
     mp.A[pl] = make_rows_map(pl ? s.in.lo : s.in.hi, s.in.pitch, a.M, 64, 128);
     mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, wrows);
