@@ -171,79 +171,76 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
 // im2col of a (B,C,px) fp32 tensor [two sources, conditional cat] into pixel-major bf16 hi/lo rows
 //   col[m][tap*C + c] = x[c][pix(m) + off(tap)]   (zero outside the image = the conv's zero padding),
 // K padded with zeros to kp (multiple of 64) except column `ones_col` (>= 0), which is 1.0.
-// thread = pixel.  Phase A walks the (tap, channel) columns of a 64-column chunk with running counters: the
-// loads of a warp are 32 consecutive pixels of one channel plane (coalesced; the 3x3 neighbours re-read L1) and
-// land in a [64 k][32 pixels] fp32 tile in shared memory.  Phase B reads the tile back row by row, splits
-// hi/lo and stores full 128-byte row segments of both planes.
-constexpr int kI2cThreads = 128;
+// thread = (pixel, 16 consecutive columns): lane = pixel, so the 16 independent loads of a thread are coalesced
+// across the warp (32 consecutive pixels of one channel plane; the 3x3 neighbours re-read L1), and each thread
+// writes one full 32-byte sector per plane.  The per-column (tap, channel) decode is a table in shared memory
+// built once per block; the per-pixel tap validity is a bit mask.
+constexpr int kI2cThreads = 256;
+constexpr int kI2cMaxK = 1024;
 __global__ void __launch_bounds__(kI2cThreads)
 k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
             long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M, int kp,
             int ones_col, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  __shared__ float stg_all[kI2cThreads / 32][64 * 33];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* stg = stg_all[wid];
-  const long long m_warp = (long long)blockIdx.x * kI2cThreads + wid * 32;
-  if (m_warp >= M) return;
-  const long long m = m_warp + lane;
-  const bool live = m < M;
-  const long long mc = live ? m : (M - 1);
-  const long long b = mc / px, pix = mc - b * px;
+  // per column: element offset relative to the pixel inside its source tensor, and (tap, which source)
+  __shared__ int s_off[kI2cMaxK];
+  __shared__ unsigned char s_tap[kI2cMaxK];  // tap index | 0x80 for the second source | 0xFF: padding column
+  for (int k = threadIdx.x; k < kp; k += blockDim.x) {
+    const int tap = k / C, ch = k - tap * C;
+    if (tap < T) {
+      int dx = 0, dy = 0, dz = 0;
+      if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
+      const bool second = ch >= c0;
+      s_off[k] = dx + dy * W + dz * W * H + (second ? ch - c0 : ch) * (int)px;
+      s_tap[k] = (unsigned char)(tap | (second ? 0x80 : 0));
+    } else {
+      s_off[k] = 0;
+      s_tap[k] = 0xFF;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long m = (long long)blockIdx.x * 32 + lane;
+  if (m >= M) return;
+  const long long b = m / px, pix = m - b * px;
   long long t = pix;
   const int x = (int)(t % W); t /= W;
   const int y = (int)(t % H); t /= H;
   const int z = (int)t;
-  const float* p0 = in0 + b * in0_bs + pix;
-  const float* p1 = in1 ? in1 + b * in1_bs + pix - (long long)c0 * px : nullptr;
-  // blockIdx.y = 64-column chunk: more parallelism when the batch shard is small, shorter threads
-  const int kc = blockIdx.y * 64;
-  int tap = kc / C, ch = kc - (kc / C) * C;  // running (tap, channel) of column k
-  bool ok = false;          // this pixel's neighbour for `tap` is inside the image
-  const float* src = p0;    // running pointer: channel `ch` of that neighbour
-  auto set_tap = [&]() {
+  uint32_t okmask = 0;  // bit tap: that neighbour is inside the image
+  for (int tap = 0; tap < T; ++tap) {
     int dx = 0, dy = 0, dz = 0;
     if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
     const int xx = x + dx, yy = y + dy, zz = z + dz;
-    ok = live && tap < T && xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D;
-    src = ((c0 > 0) ? p0 : p1) + (dx + (long long)dy * W + (long long)dz * W * H);
-  };
-  set_tap();
-  if (ch > 0 && tap < T) src = ((ch < c0) ? p0 : p1) + (src - ((c0 > 0) ? p0 : p1)) + (long long)ch * px;
-  {
-#pragma unroll 8
-    for (int j = 0; j < 64; ++j) {
-      float v = 0.f;
-      if (tap < T) {
-        if (ok) v = __ldg(src);
-        src += px;
-        if (++ch == C) { ch = 0; ++tap; set_tap(); }
-        else if (ch == c0) src = p1 + (long long)ch * px + (src - p0 - (long long)ch * px);  // switch to the second source
-      } else if (kc + j == ones_col) {
-        v = 1.f;
-      }
-      stg[j * 33 + lane] = v;
-    }
-    __syncwarp();
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 4 + (lane >> 3), k0 = (lane & 7) * 8;
-      uint32_t wh[4], wl[4];
+    if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) okmask |= 1u << tap;
+  }
+  const float* p0 = in0 + b * in0_bs + pix;
+  const float* p1 = in1 ? in1 + b * in1_bs + pix : p0;
+  for (int g = wid; g * 16 < kp; g += nw) {
+    const int k0 = g * 16;
+    float v[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float a = stg[(k0 + 2 * q) * 33 + row], bb = stg[(k0 + 2 * q + 1) * 33 + row];
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
-        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
-        wh[q] = hw;
-        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
-      }
-      if (m_warp + row < M) {
-        const long long o = (m_warp + row) * kp + kc + k0;
-        *reinterpret_cast<uint4*>(hi + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-        *reinterpret_cast<uint4*>(lo + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-      }
+    for (int j = 0; j < 16; ++j) {
+      const unsigned tp = s_tap[k0 + j];
+      const int off = s_off[k0 + j];
+      const bool ok = tp != 0xFF && ((okmask >> (tp & 31)) & 1u);
+      const float* src = (tp & 0x80) ? p1 : p0;
+      v[j] = ok ? __ldg(src + off) : ((k0 + j == ones_col) ? 1.f : 0.f);
     }
-    __syncwarp();
+    uint32_t wh[8], wl[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float a = v[2 * q], bb = v[2 * q + 1];
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+      const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
+      __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
+      wh[q] = hw;
+      wl[q] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+    const long long o = m * kp + k0;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<uint4*>(hi + o + 8) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    *reinterpret_cast<uint4*>(lo + o + 8) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
   }
 }
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
@@ -251,9 +248,14 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   if (c.dry()) return;
   const long long M = g.px * B;
   const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
+  INB_CHECK(kp <= kI2cMaxK && kp % 16 == 0, "im2col: unsupported row width %d", kp);
+  INB_CHECK((long long)C * g.px + 2 * g.px < (1ll << 31), "im2col: sample too large for 32-bit offsets");
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
-  k_im2col_tc<<<dim3((unsigned)cdiv(M, kI2cThreads), (unsigned)(kp / 64)), kI2cThreads, 0, c.st>>>(
-      in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M, kp, ones_col, out.hi, out.lo);
+  // 32 pixels per block; the warps of a block share the pixels and split the 16-column groups
+  const int groups = kp / 16;
+  const int threads = 32 * std::min(groups, 8);
+  k_im2col_tc<<<(unsigned)cdiv(M, 32), threads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
+                                                          kp, ones_col, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
 }
 

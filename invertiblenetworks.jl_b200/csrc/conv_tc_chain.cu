@@ -883,6 +883,11 @@ __device__ __forceinline__ void tma_load_2d_cg2(const void* tmap, uint32_t bar_c
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -928,23 +933,25 @@ template <int NT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChain2Threads, 1)
 k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
-  constexpr uint32_t STAGE = NP * kPlane;  // one ring stage: [<= 128 rows][64 k] per plane (per CTA)
+  constexpr uint32_t STAGE = kPlane;       // one ring granule (16 KB): a plane of an im2col block or of a GEMM3 weight
+                                           // block, or both planes of a GEMM1 / GEMM2 weight half
   constexpr uint32_t SLOT = 2 * kPlane;    // one staging slot: hi + lo planes of a 128 x 64 chunk
   constexpr int EPI = kEpi2Warps * 32;
-  // shared memory: [2 staging slots of the hidden-tensor stores][P slab staging 64 KB][ring][barriers, biases]
+  // shared memory: [2 staging slots of the hidden-tensor stores (store mode only)][P slab staging 64 KB][ring]
+  // [barriers, biases]
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stag = smem;
-  uint8_t* pstag = stag + kChain2Slots * SLOT;
+  uint8_t* pstag = stag + (a.store ? kChain2Slots * SLOT : 0);
   uint8_t* ring = pstag + 4 * kPlane;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * STAGE);
-  uint64_t* empty = full + 8;
-  uint64_t* d1h = empty + 8;      // [2]  column half h of D1 is complete
+  uint64_t* empty = full + 12;
+  uint64_t* d1h = empty + 12;     // [2]  column half h of D1 is complete
   uint64_t* d2h = d1h + 2;        // [2]  column half h of D2 is complete
   uint64_t* d3f = d2h + 2;        // [1]
   uint64_t* hready = d3f + 1;     // [4]  (leader's copy is the live one)
   uint64_t* sready = hready + 4;  // [2]
   uint64_t* sfree = sready + 2;   // [2]
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 32);  // 32 barrier slots -> 256 bytes
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 48);  // 48 barrier slots -> 384 bytes
   float* sbias = reinterpret_cast<float*>(tslot + 4);        // [2][256]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -955,6 +962,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   const int qrows = a.nh >> 2;        // weight rows of one half held by this CTA
   const int n3half = a.n3pad >> 1;    // weight rows of GEMM3 held by this CTA
   const int chalf = a.nchunk >> 1;    // chunks per column half
+  const bool w3_one = NP * n3half * 128 <= (int)kPlane;  // a GEMM3 weight block (hi + lo) fits one ring granule
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -1005,15 +1013,25 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int tp = pair0; tp < npairs; tp += pstride) {
         const int tile = 2 * tp + (int)rank;
         uint32_t bar;
-        for (int kb = 0; kb < a.nkb1; ++kb) {
-          uint8_t* st = acquire(NP * kPlane, bar);  // 128 pixels x 64 im2col columns of this CTA's tile
+        if (tp + pstride < npairs) {
+          // the im2col rows are the only operand that comes from HBM: pull the next tile's blocks into L2 a whole
+          // tile ahead (the ring's FIFO order cannot look that far)
+          const int ntile = 2 * (tp + pstride) + (int)rank;
+          for (int kb = 0; kb < a.nkb1; ++kb)
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.A[pl], bar, st + pl * kPlane, kb * 64, tile * 128);
+            for (int pl = 0; pl < NP; ++pl) tma_prefetch_2d(&maps.A[pl], kb * 64, ntile * 128);
+        }
+        for (int kb = 0; kb < a.nkb1; ++kb) {
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) {  // 128 pixels x 64 im2col columns of this CTA's tile, one plane per granule
+            uint8_t* st = acquire(kPlane, bar);
+            tma_load_2d_cg2(&maps.A[pl], bar, st, kb * 64, tile * 128);
+          }
           for (int h = 0; h < 2; ++h) {
-            st = acquire(NP * qrows * 128, bar);
+            uint8_t* st = acquire(NP * qrows * 128, bar);
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl)
-              tma_load_2d_cg2(&maps.W1[pl], bar, st + pl * kPlane, kb * 64, h * nhh + (int)rank * qrows);
+              tma_load_2d_cg2(&maps.W1[pl], bar, st + pl * qrows * 128, kb * 64, h * nhh + (int)rank * qrows);
           }
         }
         for (int h = 0; h < 2; ++h) {
@@ -1021,13 +1039,22 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             uint8_t* st = acquire(NP * qrows * 128, bar);
 #pragma unroll
             for (int pl = 0; pl < NP; ++pl)
-              tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * kPlane, c * 64, h * nhh + (int)rank * qrows);
+              tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * qrows * 128, c * 64, h * nhh + (int)rank * qrows);
           }
         }
         for (int c = 0; c < a.nchunk; ++c) {
-          uint8_t* st = acquire(NP * n3half * 128, bar);
+          if (w3_one) {  // both planes of the block fit one granule
+            uint8_t* st = acquire(NP * n3half * 128, bar);
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W3[pl], bar, st + pl * kPlane, c * 64, (int)rank * n3half);
+            for (int pl = 0; pl < NP; ++pl)
+              tma_load_2d_cg2(&maps.W3[pl], bar, st + pl * n3half * 128, c * 64, (int)rank * n3half);
+          } else {
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+              uint8_t* st = acquire(n3half * 128, bar);
+              tma_load_2d_cg2(&maps.W3[pl], bar, st, c * 64, (int)rank * n3half);
+            }
+          }
         }
       }
     }
@@ -1043,32 +1070,36 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         const int s = it % a.stages;
         const uint32_t ph = (it / a.stages) & 1;
         const long long t0 = a.trace ? clock64() : 0;
-        mbar_wait_cluster(full + s, ph);
+        mbar_wait(full + s, ph);
         if (a.trace) twait += clock64() - t0;
         tc_fence_after();
         return smem_u32(ring + (size_t)s * STAGE);
       };
-      auto mma_block_ss = [&](uint32_t d_tmem, uint32_t idesc, uint32_t a_addr, uint32_t b_addr, uint32_t first) {
-        const uint32_t alo = (a_addr >> 4) & 0x3FFF, blo = (b_addr >> 4) & 0x3FFF;
+      // operands as (hi plane, lo plane) shared-memory addresses
+      auto mma_block_ss = [&](uint32_t d_tmem, uint32_t idesc, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                              uint32_t first) {
+        const uint32_t ah = (a_hi >> 4) & 0x3FFF, al = (a_lo >> 4) & 0x3FFF;
+        const uint32_t bh = (b_hi >> 4) & 0x3FFF, bl = (b_lo >> 4) & 0x3FFF;
 #pragma unroll
         for (int term = 0; term < NT; ++term) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = ((uint64_t)dhi << 32) | (alo + ((term == 2) ? (kPlane >> 4) : 0) + 2 * k);
-            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            const uint64_t ad = ((uint64_t)dhi << 32) | (((term == 2) ? al : ah) + 2 * k);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (((term == 1) ? bl : bh) + 2 * k);
             umma2_f16(d_tmem, ad, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
           }
         }
       };
       // A = chunk c of the hidden operand in tensor memory: k-step k at column ra + 64c + 16k (hi), + 8 (lo)
-      auto mma_block_ts = [&](uint32_t d_tmem, uint32_t idesc, uint32_t ra, int c, uint32_t b_addr, uint32_t first) {
-        const uint32_t blo = (b_addr >> 4) & 0x3FFF;
+      auto mma_block_ts = [&](uint32_t d_tmem, uint32_t idesc, uint32_t ra, int c, uint32_t b_hi, uint32_t b_lo,
+                              uint32_t first) {
+        const uint32_t bh = (b_hi >> 4) & 0x3FFF, bl = (b_lo >> 4) & 0x3FFF;
 #pragma unroll
         for (int term = 0; term < NT; ++term) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t at = ra + 64 * c + 16 * k + ((term == 2) ? 8 : 0);
-            const uint64_t bd = ((uint64_t)dhi << 32) | (blo + ((term == 1) ? (kPlane >> 4) : 0) + 2 * k);
+            const uint64_t bd = ((uint64_t)dhi << 32) | (((term == 1) ? bl : bh) + 2 * k);
             umma2_f16_ts(d_tmem, at, bd, idesc, (term == 0 && k == 0) ? (first ? 0u : 1u) : 1u);
           }
         }
@@ -1082,17 +1113,26 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           tc_fence_after();
         }
         // GEMM1: both column halves per im2col block (the block stays resident while its two weight halves pass)
+        const uint32_t wlo = (uint32_t)qrows * 128;  // lo plane of a GEMM1 / GEMM2 weight half inside its granule
         for (int kb = 0; kb < a.nkb1; ++kb) {
-          const uint32_t sA = stage_wait();
-          const int slotA = it % a.stages;
+          const uint32_t aH = stage_wait();
+          const int slotH = it % a.stages;
           ++it;
+          uint32_t aL = aH;
+          int slotL = slotH;
+          if (NT == 3) {
+            aL = stage_wait();
+            slotL = it % a.stages;
+            ++it;
+          }
           for (int h = 0; h < 2; ++h, ++it) {
             const uint32_t sb = stage_wait();
-            mma_block_ss(R0 + h * nhh, idesc_12, sA, sb, kb == 0);
+            mma_block_ss(R0 + h * nhh, idesc_12, aH, aL, sb, sb + wlo, kb == 0);
             umma2_commit_mc(empty + it % a.stages);
             if (kb == a.nkb1 - 1) umma2_commit_mc(d1h + h);
           }
-          umma2_commit_mc(empty + slotA);
+          umma2_commit_mc(empty + slotH);
+          if (NT == 3) umma2_commit_mc(empty + slotL);
         }
         if (tr) { tr[1] = clock64(); tr[12] = twait; }
         twait = 0;
@@ -1100,25 +1140,35 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         for (int h = 0; h < 2; ++h) {
           for (int c = 0; c < a.nchunk; ++c, ++it) {
             if (h == 0) {
-              mbar_wait_cluster(hready + c, 0);
+              mbar_wait(hready + c, 0);
               tc_fence_after();
               if (tr && c == 0) tr[2] = clock64();
             }
             const uint32_t sb = stage_wait();
-            mma_block_ts(R1 + h * nhh, idesc_12, R0, c, sb, c == 0);
+            mma_block_ts(R1 + h * nhh, idesc_12, R0, c, sb, sb + wlo, c == 0);
             umma2_commit_mc(empty + it % a.stages);
           }
           umma2_commit_mc(d2h + h);
         }
         if (tr) { tr[3] = clock64(); tr[13] = twait; }
         twait = 0;
-        for (int c = 0; c < a.nchunk; ++c, ++it) {
-          mbar_wait_cluster(hready + c, 1);
+        for (int c = 0; c < a.nchunk; ++c) {
+          mbar_wait(hready + c, 1);
           tc_fence_after();
           if (tr && c == 0) tr[4] = clock64();
-          const uint32_t sb = stage_wait();
-          mma_block_ts(R0, idesc_3, R1, c, sb, c == 0);
-          umma2_commit_mc(empty + it % a.stages);
+          const uint32_t bH = stage_wait();
+          const int slotH = it % a.stages;
+          ++it;
+          uint32_t bL = bH + (uint32_t)n3half * 128;
+          int slotL = slotH;
+          if (NT == 3 && !w3_one) {
+            bL = stage_wait();
+            slotL = it % a.stages;
+            ++it;
+          }
+          mma_block_ts(R0, idesc_3, R1, c, bH, bL, c == 0);
+          umma2_commit_mc(empty + slotH);
+          if (NT == 3 && !w3_one) umma2_commit_mc(empty + slotL);
         }
         umma2_commit_mc(d3f);
         if (tr) { tr[5] = clock64(); tr[14] = twait; }
@@ -1487,7 +1537,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.exp = chain_exp;
   a.trace = g_chain_trace ? g_chain_trace + (size_t)(g_chain_trace_launch++ % 4) * 512 : nullptr;
   const size_t stage = (size_t)NP * kPlane, chunk = (size_t)NP * kPlane;
-  const size_t aux = 32 * 8 + 16 + 512 * 4;
+  const size_t aux = 48 * 8 + 16 + 512 * 4;
   const size_t cap = 227 * 1024;
   // kernel choice: CTA pairs (k_rb_chain2) whenever GEMM3 fits one 256-column region; INB_CHAIN_KERNEL=t|smem forces
   // the single-CTA kernels (hidden operand in tensor memory / in shared memory)
@@ -1498,14 +1548,15 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   }();
   const bool pair = a.n3pad <= 256 && force == 0;
   const bool tmem_a = a.n3pad <= 256 && force != 2;
-  const size_t fixed = pair ? (size_t)(kChain2Slots * 2 + 4) * kPlane : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
-  int stages = (int)((cap - aux - fixed) / stage);
-  if (stages > 8) stages = 8;
-  if (pair && stages > 4) stages = 4;
+  const size_t fixed = pair ? (size_t)((a.store ? kChain2Slots * 2 : 0) + 4) * kPlane
+                            : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
+  // k_rb_chain2 runs its ring in 16 KB granules (up to 12 of them)
+  int stages = (int)((cap - aux - fixed) / (pair ? (size_t)kPlane : stage));
+  if (stages > (pair ? 12 : 8)) stages = pair ? 12 : 8;
   // the im2col block of GEMM1 stays resident while the weight blocks stream past it
-  INB_CHECK(stages >= (pair ? 2 : 1 + s.nh / 128), "fused ResidualBlock chain: shared memory does not fit");
+  INB_CHECK(stages >= (pair ? 4 : 1 + s.nh / 128), "fused ResidualBlock chain: shared memory does not fit");
   a.stages = stages;
-  const size_t smem = fixed + stages * stage + aux;
+  const size_t smem = fixed + stages * (pair ? (size_t)kPlane : stage) + aux;
   ChainMaps mp{};
   const int wrows = pair ? s.nh / 4 : 128, w3rows = pair ? a.n3pad / 2 : 128;
   for (int pl = 0; pl < 2; ++pl) {
