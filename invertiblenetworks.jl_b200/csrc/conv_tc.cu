@@ -95,6 +95,21 @@ CUtensorMap make_rows_map_f32(const float* base, int pitch, long long rows, int 
   return m;
 }
 
+// fp32 [rows][pitch] tensor, box (box_c columns with box_c * 4 a multiple of 16, box_rows), no swizzle: the shared-memory
+// side is a dense [box_rows][box_c] array (Pq of the fused chain)
+CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows, int box_c, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(2, "cuTensorMapEncodeTiled(dense fp32 rows) failed with %d", (int)r);
+  return m;
+}
+
 TileBox make_tile_box(const Geo& g, int B, int P) {
   TileBox t{1, 1, 1, 1, false};
   int rem = P;
@@ -176,6 +191,7 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
 // writes one full 32-byte sector per plane.  The per-column (tap, channel) decode is a table in shared memory
 // built once per block; the per-pixel tap validity is a bit mask.
 constexpr int kI2cThreads = 256;
+constexpr int kI2cPix = 128;
 constexpr int kI2cMaxK = 1024;
 __global__ void __launch_bounds__(kI2cThreads)
 k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
@@ -198,8 +214,10 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
     }
   }
   __syncthreads();
+  // a block covers kI2cPix = 128 consecutive pixels (one table per 128 x kp outputs): warp w works on pixel segment
+  // w & 3 and takes every (nw / 4)-th 16-column group
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long m = (long long)blockIdx.x * 32 + lane;
+  const long long m = (long long)blockIdx.x * kI2cPix + (wid & 3) * 32 + lane;
   if (m >= M) return;
   const long long b = m / px, pix = m - b * px;
   long long t = pix;
@@ -215,7 +233,7 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
   }
   const float* p0 = in0 + b * in0_bs + pix;
   const float* p1 = in1 ? in1 + b * in1_bs + pix : p0;
-  for (int g = wid; g * 16 < kp; g += nw) {
+  for (int g = wid >> 2; g * 16 < kp; g += nw >> 2) {
     const int k0 = g * 16;
     float v[16];
 #pragma unroll
@@ -251,10 +269,7 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   INB_CHECK(kp <= kI2cMaxK && kp % 16 == 0, "im2col: unsupported row width %d", kp);
   INB_CHECK((long long)C * g.px + 2 * g.px < (1ll << 31), "im2col: sample too large for 32-bit offsets");
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
-  // 32 pixels per block; the warps of a block share the pixels and split the 16-column groups
-  const int groups = kp / 16;
-  const int threads = 32 * std::min(groups, 8);
-  k_im2col_tc<<<(unsigned)cdiv(M, 32), threads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
+  k_im2col_tc<<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
                                                           kp, ones_col, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
 }

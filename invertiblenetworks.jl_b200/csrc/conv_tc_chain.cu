@@ -45,6 +45,10 @@ struct ChainArgs {
   int n3a, n3b, n3pad;    // GEMM3 columns in R0 / R1 and the pitch of P (multiple of 16)
   int np3;                // 128-column pieces of GEMM3
   int stages;
+  // k_rb_chain2 with qsum: E3 sums the three horizontal taps of every (dy[,dz]) tap row on the SM, so P shrinks from
+  // taps*Cn to (taps/3)*cq columns per pixel (Pq[m][tg*cq + n], cq = Cn rounded up to 4, pitch nq = (taps/3)*cq)
+  int qsum, Cn, cq, nq, ntg;
+  int pstag_bytes;        // k_rb_chain2: size of the P staging area
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
@@ -834,6 +838,9 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
 // (cp.async.bulk.tensor ... cta_group::2), the leader's producer posts the expect_tx for both; stage release and
 // accumulator-ready signals are tcgen05.commit.cta_group::2 multicast to both CTAs; "hidden operand ready" is
 // counted on the leader's barrier by the epilogue warps of both CTAs (remote mbarrier.arrive).
+// The hidden tensors of a storing pass are staged chunk by chunk in two shared-memory slots and leave with TMA stores.
+// (Writing them straight from the registers - one 32-byte sector per thread and plane with 256-bit stores - was tried:
+// a warp's 32 sectors are 32 separate L1 transactions, and the storing passes became 1.5x slower.)
 // Warps: 0 TMA producer | 1 MMA issuer (leader only) | 2..17 epilogue | 18 TMA store of the hidden tensors.
 constexpr int kEpi2Warps = 16;
 constexpr int kChain2Threads = 32 * (2 + kEpi2Warps + 1);
@@ -929,7 +936,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <int NT>
+template <int NT, bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChain2Threads, 1)
 k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
@@ -937,12 +944,11 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
                                            // block, or both planes of a GEMM1 / GEMM2 weight half
   constexpr uint32_t SLOT = 2 * kPlane;    // one staging slot: hi + lo planes of a 128 x 64 chunk
   constexpr int EPI = kEpi2Warps * 32;
-  // shared memory: [2 staging slots of the hidden-tensor stores (store mode only)][P slab staging 64 KB][ring]
-  // [barriers, biases]
+  // shared memory: [2 staging slots of the hidden-tensor stores (store mode only)][P staging][ring][barriers, biases]
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stag = smem;
   uint8_t* pstag = stag + (a.store ? kChain2Slots * SLOT : 0);
-  uint8_t* ring = pstag + 4 * kPlane;
+  uint8_t* ring = pstag + a.pstag_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.stages * STAGE);
   uint64_t* empty = full + 12;
   uint64_t* d1h = empty + 12;     // [2]  column half h of D1 is complete
@@ -1069,9 +1075,9 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       auto stage_wait = [&]() -> uint32_t {
         const int s = it % a.stages;
         const uint32_t ph = (it / a.stages) & 1;
-        const long long t0 = a.trace ? clock64() : 0;
+        const long long t0 = (TRACE && a.trace) ? clock64() : 0;
         mbar_wait(full + s, ph);
-        if (a.trace) twait += clock64() - t0;
+        if (TRACE && a.trace) twait += clock64() - t0;
         tc_fence_after();
         return smem_u32(ring + (size_t)s * STAGE);
       };
@@ -1106,7 +1112,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       };
       for (int tp = pair0; tp < npairs; tp += pstride, ++tl) {
         const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
-        long long* tr = (a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
+        long long* tr = (TRACE && a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
         if (tr) tr[0] = clock64();
         if (tl > 0) {  // R0 held the A operand of the previous pair's GEMM3: let those MMAs retire first
           mbar_wait(d3f, (tl - 1) & 1);
@@ -1191,7 +1197,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
       const long long m = (long long)tile * 128 + row;
       const bool live = m < a.M;
-      long long* tr = (a.trace && blockIdx.x == 0 && tl < 16 && e == 0 && lane == 0) ? a.trace + tl * 16 + 6 : nullptr;
+      long long* tr = (TRACE && a.trace && blockIdx.x == 0 && tl < 16 && e == 0 && lane == 0) ? a.trace + tl * 16 + 6 : nullptr;
 #pragma unroll 1
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t reg = (stg ? R1 : R0) + lane_sel + 16 * kk;
@@ -1199,21 +1205,16 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         const long long hrow = m * (a.nh >> 4) + kk;  // 16-bit word 4c + kk of the row's bit plane
         const uint16_t* mk = reinterpret_cast<const uint16_t*>(stg ? a.mask2 : a.mask1) + hrow;
         uint16_t* bo = reinterpret_cast<uint16_t*>(stg ? a.bits2 : a.bits1) + hrow;
+
         uint64_t* dh = stg ? d2h : d1h;
         uint32_t mA = 0, mB = 0;
         if (a.mode == 1) mA = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk) : 0u;  // chunk 0's mask, before the wait
         mbar_wait(dh + 0, tl & 1);
         tc_fence_after();
         if (tr) tr[2 * stg] = clock64();
-        uint32_t rA[16], rB[16];
-        auto fetch = [&](int c, uint32_t (&r)[16], uint32_t& mm) {
-          if (c == chalf) {  // first chunk of the second column half
-            mbar_wait(dh + 1, tl & 1);
-            tc_fence_after();
-          }
-          if (a.mode == 1 && c > 0) mm = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk + 4 * c) : 0u;
-          tmem_ld16(reg + 64 * c, r);
-        };
+        // one chunk at a time (no register double buffer: four epilogue warps per scheduler hide the TMEM load latency, and
+        // the kernel has 96 registers per thread)
+        uint32_t rA[16];
         auto emit = [&](int c, const uint32_t (&r)[16], const uint32_t mm) {
           uint32_t wh[8], wl[8];
           uint32_t bits = 0;
@@ -1257,21 +1258,17 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             if (a.store) mbar_arrive(sready + slot);
           }
         };
-        fetch(0, rA, mA);
 #pragma unroll 1
-        for (int c = 0; c < a.nchunk; c += 2) {
-          // the next chunk's TMEM load is issued before this chunk is converted - unless it belongs to the second
-          // column half, whose completion must not hold up the hand-over of this chunk
+        for (int c = 0; c < a.nchunk; ++c) {
+          if (c == chalf) {  // first chunk of the second column half
+            mbar_wait(dh + 1, tl & 1);
+            tc_fence_after();
+          }
+          tmem_ld16(reg + 64 * c, rA);
+          if (a.mode == 1 && c + 1 < a.nchunk) mB = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk + 4 * (c + 1)) : 0u;
           tmem_ld_wait();
-          const bool late1 = (c + 1 == chalf);
-          if (!late1) fetch(c + 1, rB, mB);
           emit(c, rA, mA);
-          if (late1) fetch(c + 1, rB, mB);
-          tmem_ld_wait();
-          const bool more = c + 2 < a.nchunk, late2 = (c + 2 == chalf);
-          if (more && !late2) fetch(c + 2, rA, mA);
-          emit(c + 1, rB, mB);
-          if (more && late2) fetch(c + 2, rA, mA);
+          mA = mB;
         }
         if (tr) tr[2 * stg + 1] = clock64();
       }
@@ -1279,6 +1276,104 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       mbar_wait(d3f, tl & 1);
       tc_fence_after();
       if (tr) tr[4] = clock64();
+      if (a.qsum) {
+        // D3 rows -> plain fp32 rows in shared memory; then every (pixel, tap row, 4 channels) item adds its three
+        // horizontal taps: Q[(y', x)][tg][n] = sum_dx D3[(y', x + dx)][(3 tg + dx + 1) Cn + n] (x + dx inside the image
+        // row; a tile is whole image rows because 128 % W == 0); col2im then only sums over tap rows
+        float* raw = reinterpret_cast<float*>(pstag);
+        const int rp = a.n3pad + 4;  // row pitch in floats: 16-byte accesses of consecutive rows hit distinct banks
+        float* qst = raw + 128 * rp;  // dense [128][nq], the box of the (unswizzled) TMA store
+        long long* tq = (TRACE && tr && tl == 2) ? a.trace + 256 : nullptr;  // fine-grained E3 timeline of one thread
+        if (tq) tq[0] = clock64();
+        if (tl > 0 && tid == 0) bulk_wait_read0();  // the previous tile's Pq store has read qst
+        if (tq) tq[1] = clock64();
+        {
+          const int c0 = 32 * kk;
+          float* dst = raw + row * rp + c0;
+          if (c0 + 32 <= a.n3pad) {
+            uint32_t r[32];
+            tmem_ld32(R0 + lane_sel + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          } else if (c0 < a.n3pad) {
+            uint32_t r[16];
+            tmem_ld16(R0 + lane_sel + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        }
+        if (tq) tq[2] = clock64();
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        if (tq) tq[3] = clock64();
+        // items (pixel r, tap row tg, 4-channel group g), decoded with shifts and one multiply (W is a power of two,
+        // tg = rest / ngrp through a 16-bit reciprocal): nothing is kept in registers across tiles
+        const int nstep = rp + a.Cn;  // neighbour row, neighbour tap
+        const int ngrp = a.cq >> 2, items = 128 * a.ntg * ngrp;
+        const uint32_t inv = 65536u / (uint32_t)ngrp + 1u;
+        const int vmode = ((a.Cn & 3) == 0) ? 4 : (((a.Cn & 1) == 0) ? 2 : 1);
+#pragma unroll 1
+        for (int i = tid; i < items; i += EPI) {
+          const int r = i & 127, rest = i >> 7;
+          const int tg = (int)(((uint32_t)rest * inv) >> 16), g = rest - tg * ngrp;
+          const int x = r & (a.W - 1);
+          const bool left = x > 0, right = x + 1 < a.W;
+          const float* ctr = raw + r * rp + (tg * 3 + 1) * a.Cn + 4 * g;  // centre tap of this item's tap row
+          float4 acc;
+          if (vmode == 4) {
+            acc = *reinterpret_cast<const float4*>(ctr);
+            if (left) {
+              const float4 v = *reinterpret_cast<const float4*>(ctr - nstep);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (right) {
+              const float4 v = *reinterpret_cast<const float4*>(ctr + nstep);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+          } else if (vmode == 2) {
+            const bool hi2 = 4 * g + 2 < a.Cn;
+            float2 a0 = *reinterpret_cast<const float2*>(ctr);
+            float2 a1 = hi2 ? *reinterpret_cast<const float2*>(ctr + 2) : make_float2(0.f, 0.f);
+            if (left) {
+              const float2 v0 = *reinterpret_cast<const float2*>(ctr - nstep);
+              a0.x += v0.x; a0.y += v0.y;
+              if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr - nstep + 2); a1.x += v1.x; a1.y += v1.y; }
+            }
+            if (right) {
+              const float2 v0 = *reinterpret_cast<const float2*>(ctr + nstep);
+              a0.x += v0.x; a0.y += v0.y;
+              if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr + nstep + 2); a1.x += v1.x; a1.y += v1.y; }
+            }
+            acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+          } else {
+            float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              if ((dxi == 0 && !left) || (dxi == 2 && !right)) continue;
+              const float* src = ctr + (dxi - 1) * nstep;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (4 * g + u < a.Cn) t4[u] += src[u];
+            }
+            acc = make_float4(t4[0], t4[1], t4[2], t4[3]);
+          }
+          *reinterpret_cast<float4*>(qst + r * a.nq + tg * a.cq + 4 * g) = acc;
+        }
+        if (tq) tq[4] = clock64();
+        fence_proxy_async();
+        if (tq) tq[5] = clock64();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        if (tq) tq[6] = clock64();
+        if (tid == 0) {
+          tma_store_2d(&maps.P, qst, 0, tile * 128);
+          bulk_commit();
+        }
+        if (tq) tq[7] = clock64();
+      } else
 #pragma unroll 1
       for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
         const int ncols = min(128, a.n3pad - slab * 128);
@@ -1358,6 +1453,8 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
 // out[b][n][pix] = sum_tap P[pix + off(tap)][tap*Cn + n]  (+ passthrough add), coalesced both ways through a
 // shared-memory transpose: phase 1 walks (pixel, n) with n fastest (contiguous in P), phase 2 walks pixels.
 struct Col2imArgs {
+  int qsum;  // P holds tap-ROW sums (k_rb_chain2 with qsum): `taps` counts tap rows, column = row * cstride + n
+  int cstride;
   int W, H, D, ksz, taps, Cn, n3pad;
   long long px, M;
   const float* P;
@@ -1365,68 +1462,57 @@ struct Col2imArgs {
   float* out1; long long out1_bs; int out1_accum;
   const float* add; long long add_bs; int add_n;
 };
-constexpr int kC2iPix = 64;
-
+// thread = pixel: every tap (or tap row) contributes V-wide vectors of the pixel's P row, the sums stay in registers
+// (16 channels at a time) and each channel is stored with the warp's 32 consecutive pixels (coalesced both ways, no
+// shared memory; the 144-byte row stride of the loads is absorbed by L1, every byte of a row is used)
 template <int V>
-__global__ void __launch_bounds__(256) k_col2im(const Col2imArgs a) {
-  extern __shared__ float c2i_s[];  // [Cn][kC2iPix + 1]
-  const long long m0 = (long long)blockIdx.x * kC2iPix;
-  const int ng = a.Cn / V;  // V consecutive channels per item: lanes walk the channels of a P row first
-  for (int i = threadIdx.x; i < kC2iPix * ng; i += blockDim.x) {
-    const int p = i / ng, g = i - p * ng;
-    const long long m = m0 + p;
-    float acc[V];
+__global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.M) return;
+  const long long b = m / a.px, pix = m - b * a.px;
+  long long t = pix;
+  const int x = (int)(t % a.W); t /= a.W;
+  const int y = (int)(t % a.H); t /= a.H;
+  const int z = (int)t;
+  for (int c0 = 0; c0 < a.Cn; c0 += 16) {
+    float acc[16];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    if (m < a.M) {
-      long long t = m;
-      const int x = (int)(t % a.W); t /= a.W;
-      const int y = (int)(t % a.H); t /= a.H;
-      const int z = (int)(t % a.D);
-      const float* base = a.P + m * a.n3pad + g * V;
-      // taps in batches of 9: all loads of a batch are issued before the first add (memory-level parallelism)
-      for (int t0 = 0; t0 < a.taps; t0 += 9) {
-        float q[9][V];
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int tap = 0; tap < a.taps; ++tap) {
+      int dx, dy, dz;
+      if (a.qsum) { dx = 0; dy = tap % 3 - 1; dz = (a.D > 1) ? tap / 3 - 1 : 0; }
+      else chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
+      const int xx = x + dx, yy = y + dy, zz = z + dz;
+      if (xx < 0 || xx >= a.W || yy < 0 || yy >= a.H || zz < 0 || zz >= a.D) continue;
+      const float* src = a.P + (m + dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.cstride + c0;
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
-          const int tap = t0 + j;
-          int dx, dy, dz;
-          chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
-          const int xx = x + dx, yy = y + dy, zz = z + dz;
-          const bool ok = tap < a.taps && xx >= 0 && xx < a.W && yy >= 0 && yy < a.H && zz >= 0 && zz < a.D;
-          const float* src = base + (dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.Cn;
+      for (int j = 0; j < 16; j += V) {
+        if (c0 + j < a.Cn) {
           if (V == 4) {
-            const float4 w = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            q[j][0] = w.x; q[j][1 % V] = w.y; q[j][2 % V] = w.z; q[j][3 % V] = w.w;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(src + j));
+            acc[j] += w.x; acc[(j + 1) % 16] += w.y; acc[(j + 2) % 16] += w.z; acc[(j + 3) % 16] += w.w;
           } else if (V == 2) {
-            const float2 w = ok ? __ldg(reinterpret_cast<const float2*>(src)) : make_float2(0.f, 0.f);
-            q[j][0] = w.x; q[j][1 % V] = w.y;
+            const float2 w = __ldg(reinterpret_cast<const float2*>(src + j));
+            acc[j] += w.x; acc[(j + 1) % 16] += w.y;
           } else {
-            q[j][0] = ok ? __ldg(src) : 0.f;
+            acc[j] += __ldg(src + j);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 9; ++j)
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[v] += q[j][v];
       }
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v) c2i_s[(g * V + v) * (kC2iPix + 1) + p] = acc[v];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kC2iPix * a.Cn; i += blockDim.x) {
-    const int n = i / kC2iPix, p = i - n * kC2iPix;
-    const long long m = m0 + p;
-    if (m >= a.M) continue;
-    const long long b = m / a.px, pix = m - b * a.px;
-    float v = c2i_s[n * (kC2iPix + 1) + p];
-    if (a.add && n < a.add_n) v += a.add[b * a.add_bs + (long long)n * a.px + pix];
-    if (n < a.n0) {
-      a.out0[b * a.out0_bs + (long long)n * a.px + pix] = v;
-    } else {
-      float* qq = a.out1 + b * a.out1_bs + (long long)(n - a.n0) * a.px + pix;
-      *qq = a.out1_accum ? (*qq + v) : v;
+    for (int j = 0; j < 16; ++j) {
+      const int n = c0 + j;
+      if (n < a.Cn) {
+        float v = acc[j];
+        if (a.add && n < a.add_n) v += a.add[b * a.add_bs + (long long)n * a.px + pix];
+        if (n < a.n0) {
+          a.out0[b * a.out0_bs + (long long)n * a.px + pix] = v;
+        } else {
+          float* qq = a.out1 + b * a.out1_bs + (long long)(n - a.n0) * a.px + pix;
+          *qq = a.out1_accum ? (*qq + v) : v;
+        }
+      }
     }
   }
 }
@@ -1547,8 +1633,15 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
   }();
   const bool pair = a.n3pad <= 256 && force == 0;
+  static const bool no_qsum = [] { const char* e = getenv("INB_CHAIN_QSUM"); return e && e[0] == '0'; }();
+  a.Cn = s.Cn;
+  a.cq = (s.Cn + 3) / 4 * 4;
+  a.ntg = taps / 3;
+  a.nq = a.ntg * a.cq;
+  a.qsum = (pair && !no_qsum && taps >= 9 && 128 % s.g.W == 0 && (s.g.W & (s.g.W - 1)) == 0 && a.n3pad <= 128) ? 1 : 0;
+  a.pstag_bytes = a.qsum ? (int)((((size_t)128 * (a.n3pad + 4) + (size_t)128 * a.nq) * 4 + 1023) / 1024 * 1024) : 4 * (int)kPlane;
   const bool tmem_a = a.n3pad <= 256 && force != 2;
-  const size_t fixed = pair ? (size_t)((a.store ? kChain2Slots * 2 : 0) + 4) * kPlane
+  const size_t fixed = pair ? (size_t)(a.store ? kChain2Slots * 2 : 0) * kPlane + a.pstag_bytes
                             : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
   // k_rb_chain2 runs its ring in 16 KB granules (up to 12 of them)
   int stages = (int)((cap - aux - fixed) / (pair ? (size_t)kPlane : stage));
@@ -1572,17 +1665,18 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
       mp.O2[pl] = mp.W2[pl];
     }
   }
-  mp.P = make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
+  mp.P = a.qsum ? make_rows_map_f32_dense(s.P, a.nq, a.M, a.nq, 128) : make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
   unsigned grid = (unsigned)std::min(a.ntiles, 148);
   const double flops = 2.0 * a.M * ((double)s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
   {
     Prof pf(c, F_CONV_TC, 1, flops, 0);
     if (pair) {
-      auto kern = (NT == 3) ? k_rb_chain2<3> : k_rb_chain2<1>;
+      auto kern = a.trace ? ((NT == 3) ? k_rb_chain2<3, true> : k_rb_chain2<1, true>)
+                          : ((NT == 3) ? k_rb_chain2<3, false> : k_rb_chain2<1, false>);
       INB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // resident CTA pairs: one CTA per SM, pairs are placed inside a GPC (the query accounts for odd GPCs)
-      static int max_pairs[2] = {0, 0};
-      int& mpairs = max_pairs[NT == 3];
+      static int max_pairs[4] = {0, 0, 0, 0};
+      int& mpairs = max_pairs[(NT == 3) + 2 * (a.trace != nullptr)];
       if (mpairs == 0) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(148);
@@ -1617,16 +1711,19 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   {
     Col2imArgs ca{};
     ca.W = s.g.W; ca.H = s.g.H; ca.D = s.g.D; ca.ksz = s.k1; ca.taps = taps; ca.Cn = s.Cn; ca.n3pad = a.n3pad;
+    ca.qsum = a.qsum; ca.cstride = s.Cn;
+    if (a.qsum) { ca.taps = a.ntg; ca.n3pad = a.nq; ca.cstride = a.cq; }
     ca.px = s.g.px; ca.M = a.M; ca.P = s.P;
     ca.out0 = s.out0; ca.out0_bs = s.out0_bs; ca.n0 = s.n0;
     ca.out1 = s.out1; ca.out1_bs = s.out1_bs; ca.out1_accum = s.out1_accum;
     ca.add = s.add; ca.add_bs = s.add_bs; ca.add_n = s.add_n;
-    Prof pf(c, F_COL2IM, 1, 0, (4.0 * a.n3pad + 4.0 * s.Cn) * a.M);
-    const size_t sm = (size_t)s.Cn * (kC2iPix + 1) * sizeof(float);
-    const unsigned nb = (unsigned)cdiv(a.M, kC2iPix);
-    if (s.Cn % 4 == 0) k_col2im<4><<<nb, 256, sm, c.st>>>(ca);
-    else if (s.Cn % 2 == 0) k_col2im<2><<<nb, 256, sm, c.st>>>(ca);
-    else k_col2im<1><<<nb, 256, sm, c.st>>>(ca);
+    Prof pf(c, F_COL2IM, 1, 0, (4.0 * ca.n3pad + 4.0 * s.Cn) * a.M);
+    const unsigned nb = (unsigned)cdiv(a.M, 128);
+    const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;
+    const bool v2 = s.Cn % 2 == 0 && ca.cstride % 2 == 0 && ca.n3pad % 2 == 0;
+    if (v4) k_col2im<4><<<nb, 128, 0, c.st>>>(ca);
+    else if (v2) k_col2im<2><<<nb, 128, 0, c.st>>>(ca);
+    else k_col2im<1><<<nb, 128, 0, c.st>>>(ca);
     INB_CUDA(cudaGetLastError());
   }
 }

@@ -11,4 +11,5 @@ CUtensorMap make_w_map(const __nv_bfloat16* base, int ktot, int rows, int ck);
 // generic [rows][pitch] bf16 planes, box (box_c channels, box_rows rows), swizzle = box_c*2 bytes
 CUtensorMap make_rows_map(const __nv_bfloat16* base, int pitch, long long rows, int box_c, int box_rows);
 CUtensorMap make_rows_map_f32(const float* base, int pitch, long long rows, int box_c, int box_rows);
+CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows, int box_c, int box_rows);
 }  // namespace inb

@@ -33,11 +33,8 @@ for li, title in enumerate(["forward (no store)", "recompute (stores H1, H2)", "
         v = [(x.item() - t0) for x in r[:12]]
         print(" ".join(str(x).rjust(8) for x in v[:6]) + "        | " + " ".join(str(x).rjust(8) for x in v[6:12]),
               "| TMA waits G1/G2/G3", r[12].item(), r[13].item(), r[14].item())
-    fine = t[16:24, :9]
-    if fine[0, 0].item():
-        print("  epilogue warp 0, third tile: per chunk (E1 c0..3, E2 c0..3), cycles relative to the tile's d1full:")
-        print("  " + " ".join(n.rjust(8) for n in ["ldwait0", "ldwait1", "emit", "packed", "st_iss", "sfree", "staged", "st_done", "arrived"]))
-        base = t[2, 6].item()
-        for rr in fine:
-            v = [rr[7].item(), rr[8].item(), rr[0].item(), rr[1].item(), rr[2].item(), rr[3].item(), rr[4].item(), rr[5].item(), rr[6].item()]
-            print("  " + " ".join((str(x - base) if x else "-").rjust(8) for x in v))
+    f = t[16, :8]
+    if f[0].item():
+        names3 = ["start", "pq_read", "staged", "bar1", "summed", "fenced", "bar2", "issued"]
+        print("  E3 of the third tile (thread 0), cycles after d3full: " +
+              ", ".join(f"{n} {f[k].item() - t[2, 10].item()}" for k, n in enumerate(names3)))
