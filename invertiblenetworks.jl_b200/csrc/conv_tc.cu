@@ -186,13 +186,16 @@ void op_nchw_to_tc(Ctx& c, const Geo& g, int B, const float* in0, long long in0_
 // im2col of a (B,C,px) fp32 tensor [two sources, conditional cat] into pixel-major bf16 hi/lo rows
 //   col[m][tap*C + c] = x[c][pix(m) + off(tap)]   (zero outside the image = the conv's zero padding),
 // K padded with zeros to kp (multiple of 64) except column `ones_col` (>= 0), which is 1.0.
-// thread = (pixel, 16 consecutive columns): lane = pixel, so the 16 independent loads of a thread are coalesced
-// across the warp (32 consecutive pixels of one channel plane; the 3x3 neighbours re-read L1), and each thread
-// writes one full 32-byte sector per plane.  The per-column (tap, channel) decode is a table in shared memory
-// built once per block; the per-pixel tap validity is a bit mask.
-constexpr int kI2cThreads = 256;
+// warp = 32 consecutive pixels (lane = pixel) x one 64-column block at a time.  Gather phase: the 16 independent loads
+// of a (pixel, 16-column group) are coalesced across the warp (32 consecutive pixels of one channel plane; the 3x3
+// neighbours re-read L1); hi / lo words go to a [32 rows][128 B + 16] tile per plane in shared memory.  Store phase:
+// the tile leaves as full 128-byte rows (4 rows per warp instruction).  Storing straight from the gather layout costs
+// one L1 transaction per lane (32 per instruction) and made the kernel transaction-bound at a third of HBM speed.
+// The per-column (tap, channel) decode is a table built once per block; the per-pixel tap validity is a bit mask.
+constexpr int kI2cThreads = 128;
 constexpr int kI2cPix = 128;
 constexpr int kI2cMaxK = 1024;
+constexpr int kI2cRow = 144;  // bytes per tile row: 16-byte chunks of consecutive rows fall into different banks
 __global__ void __launch_bounds__(kI2cThreads)
 k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
             long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M, int kp,
@@ -200,6 +203,7 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
   // per column: element offset relative to the pixel inside its source tensor, and (tap, which source)
   __shared__ int s_off[kI2cMaxK];
   __shared__ unsigned char s_tap[kI2cMaxK];  // tap index | 0x80 for the second source | 0xFF: padding column
+  __shared__ __align__(16) unsigned char s_tile[kI2cThreads / 32][2][32 * kI2cRow];
   for (int k = threadIdx.x; k < kp; k += blockDim.x) {
     const int tap = k / C, ch = k - tap * C;
     if (tap < T) {
@@ -214,51 +218,70 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
     }
   }
   __syncthreads();
-  // a block covers kI2cPix = 128 consecutive pixels (one table per 128 x kp outputs): warp w works on pixel segment
-  // w & 3 and takes every (nw / 4)-th 16-column group
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const long long m = (long long)blockIdx.x * kI2cPix + (wid & 3) * 32 + lane;
-  if (m >= M) return;
-  const long long b = m / px, pix = m - b * px;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long m0 = (long long)blockIdx.x * kI2cPix + wid * 32;  // first pixel of this warp
+  if (m0 >= M) return;
+  const long long m = m0 + lane;
+  const bool live = m < M;
+  const long long mc = live ? m : M - 1;
+  const long long b = mc / px, pix = mc - b * px;
   long long t = pix;
   const int x = (int)(t % W); t /= W;
   const int y = (int)(t % H); t /= H;
   const int z = (int)t;
   uint32_t okmask = 0;  // bit tap: that neighbour is inside the image
-  for (int tap = 0; tap < T; ++tap) {
-    int dx = 0, dy = 0, dz = 0;
-    if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
-    const int xx = x + dx, yy = y + dy, zz = z + dz;
-    if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) okmask |= 1u << tap;
+  if (live) {
+    for (int tap = 0; tap < T; ++tap) {
+      int dx = 0, dy = 0, dz = 0;
+      if (ksz != 1) { dx = tap % 3 - 1; dy = (tap / 3) % 3 - 1; dz = (D > 1) ? tap / 9 - 1 : 0; }
+      const int xx = x + dx, yy = y + dy, zz = z + dz;
+      if (xx >= 0 && xx < W && yy >= 0 && yy < H && zz >= 0 && zz < D) okmask |= 1u << tap;
+    }
   }
   const float* p0 = in0 + b * in0_bs + pix;
   const float* p1 = in1 ? in1 + b * in1_bs + pix : p0;
-  for (int g = wid >> 2; g * 16 < kp; g += nw >> 2) {
-    const int k0 = g * 16;
-    float v[16];
+  unsigned char* th = s_tile[wid][0];
+  unsigned char* tl = s_tile[wid][1];
+  for (int kb = 0; kb < kp; kb += 64) {
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      const int k0 = kb + g * 16;
+      float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const unsigned tp = s_tap[k0 + j];
-      const int off = s_off[k0 + j];
-      const bool ok = tp != 0xFF && ((okmask >> (tp & 31)) & 1u);
-      const float* src = (tp & 0x80) ? p1 : p0;
-      v[j] = ok ? __ldg(src + off) : ((k0 + j == ones_col) ? 1.f : 0.f);
-    }
-    uint32_t wh[8], wl[8];
+      for (int j = 0; j < 16; ++j) {
+        const unsigned tp = s_tap[k0 + j];
+        const int off = s_off[k0 + j];
+        const bool ok = tp != 0xFF && ((okmask >> (tp & 31)) & 1u);
+        const float* src = (tp & 0x80) ? p1 : p0;
+        v[j] = ok ? __ldg(src + off) : ((k0 + j == ones_col) ? 1.f : 0.f);
+      }
+      uint32_t wh[8], wl[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float a = v[2 * q], bb = v[2 * q + 1];
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-      const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
-      __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
-      wh[q] = hw;
-      wl[q] = *reinterpret_cast<uint32_t*>(&l2);
+      for (int q = 0; q < 8; ++q) {
+        const float a = v[2 * q], bb = v[2 * q + 1];
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
+        wh[q] = hw;
+        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
+      }
+      const int o = lane * kI2cRow + g * 32;
+      *reinterpret_cast<uint4*>(th + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      *reinterpret_cast<uint4*>(th + o + 16) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+      *reinterpret_cast<uint4*>(tl + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      *reinterpret_cast<uint4*>(tl + o + 16) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
     }
-    const long long o = m * kp + k0;
-    *reinterpret_cast<uint4*>(hi + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-    *reinterpret_cast<uint4*>(hi + o + 8) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
-    *reinterpret_cast<uint4*>(lo + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-    *reinterpret_cast<uint4*>(lo + o + 8) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int id = it * 32 + lane, row = id >> 3, ch = id & 7;
+      if (m0 + row < M) {
+        const long long o = (m0 + row) * kp + kb + ch * 8;
+        *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(th + row * kI2cRow + ch * 16);
+        *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(tl + row * kI2cRow + ch * 16);
+      }
+    }
+    __syncwarp();
   }
 }
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
@@ -266,7 +289,7 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   if (c.dry()) return;
   const long long M = g.px * B;
   const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
-  INB_CHECK(kp <= kI2cMaxK && kp % 16 == 0, "im2col: unsupported row width %d", kp);
+  INB_CHECK(kp <= kI2cMaxK && kp % 64 == 0, "im2col: unsupported row width %d", kp);
   INB_CHECK((long long)C * g.px + 2 * g.px < (1ll << 31), "im2col: sample too large for 32-bit offsets");
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
   k_im2col_tc<<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
