@@ -352,6 +352,14 @@ def main():
             achieved = top["bytes"] / (top["ms"] / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": achieved / pk["hbm"], "traffic": None, "peak_source": pk["src"]}
+        # dram bytes per launch of that kernel from the committed ncu --set full capture (profiles/r01_traffic.json)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+                tr = json.load(fh)
+            roof["traffic"] = tr[top["name"]].get("traffic_bytes_per_launch_mean")
+            roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         roof["launches"] = top["scopes"]
         roof["avg_launch_ms"] = per_launch_ms
         roof["share_of_step"] = top["ms"] / ms_prof
