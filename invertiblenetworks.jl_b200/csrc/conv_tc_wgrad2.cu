@@ -192,7 +192,8 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p]; fixed summation order
+// dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p]; fixed summation order (eight
+// interleaved partial sums per output keep eight loads in flight: the kernel is a latency-bound column walk)
 __global__ void k_wgrad_reduce(const float* __restrict__ part, int ncta, int np, int pitch, int qtot, int C, int T,
                                float* __restrict__ dw, const float* __restrict__ dbpart, float* __restrict__ db) {
   const int ncol = T * C;
@@ -201,16 +202,26 @@ __global__ void k_wgrad_reduce(const float* __restrict__ part, int ncta, int np,
        i += (long long)gridDim.x * blockDim.x) {
     if (i >= total) {
       const int p = (int)(i - total);
-      float s = 0.f;
-      for (int k = 0; k < ncta; ++k) s += dbpart[(long long)k * np + p];
-      db[p] = s;
+      float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int k = 0;
+      for (; k + 8 <= ncta; k += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s8[u] += dbpart[(long long)(k + u) * np + p];
+      for (; k < ncta; ++k) s8[0] += dbpart[(long long)k * np + p];
+      db[p] = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
       continue;
     }
     const int col = (int)(i % ncol), p = (int)(i / ncol);
     const int g = col >> 8, cg = col & 255;
     const float* src = part + ((long long)g * ncta * np + p) * pitch + cg;
-    float s = 0.f;
-    for (int k = 0; k < ncta; ++k) s += src[(long long)k * np * pitch];
+    const long long stride = (long long)np * pitch;
+    float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int k = 0;
+    for (; k + 8 <= ncta; k += 8)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s8[u] += __ldg(src + (k + u) * stride);
+    for (; k < ncta; ++k) s8[0] += __ldg(src + k * stride);
+    const float s = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
     const int tap = col / C, cc = col - tap * C;
     dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
   }
