@@ -1691,7 +1691,12 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 64; }
         mpairs = std::min(n, 74);
       }
-      grid = 2u * (unsigned)std::min((a.ntiles + 1) / 2, mpairs);
+      int use_pairs = mpairs;
+      if (const char* e = getenv("INB_CHAIN_MAXPAIRS")) {  // tests: few resident pairs = many tiles per pair on small inputs
+        const int v = atoi(e);
+        if (v > 0 && v < use_pairs) use_pairs = v;
+      }
+      grid = 2u * (unsigned)std::min((a.ntiles + 1) / 2, use_pairs);
       kern<<<grid, kChain2Threads, smem, c.st>>>(mp, a);
     } else if (tmem_a && NT == 3) {
       INB_CUDA(cudaFuncSetAttribute(k_rb_chain_t<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

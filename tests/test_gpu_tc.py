@@ -88,6 +88,20 @@ def test_coupling_layer_tc(case, prec):
         assert_grad_close(p.grad, q.grad, tol_grad, fr, name)
 
 
+@pytest.mark.parametrize("case", [
+    (4, 6, 256, 12, (32, 32)),     # cfg2 scale-1 channel plan, 4 image rows per tile
+    (3, 12, 256, 24, (64, 64)),    # scale-2 plan: GEMM3 wider than 128 columns (full P path), 2 rows per tile
+    (5, 6, 128, 12, (16, 16)),     # odd number of tiles: the last pair has an empty tile
+    (2, 24, 256, 48, (32, 32)),    # scale-3 plan: forward on the single-CTA kernel, backward on pairs
+])
+def test_resblock_tc_many_tiles_per_pair(case, monkeypatch):
+    """The persistent loop of the CTA-pair kernel (ring wrap, barrier parities, TMEM region swap, staging reuse)
+    over many tiles per pair: the number of resident pairs is capped at 2, so a small input already walks 4-16
+    tile pairs per cluster."""
+    monkeypatch.setenv("INB_CHAIN_MAXPAIRS", "2")
+    test_resblock_tc(case + (3, 1), "bf16x3")
+
+
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 def test_glow_network_tc(prec):
     """cfg2's channel plan (3 -> 12/24/48) with n_hidden = 128 at 64x64, L = 3."""
