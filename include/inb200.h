@@ -163,6 +163,12 @@ int inb_unsqueeze(int ndims, int nx, int ny, int nz, int B, int C, const float* 
  * loss = sum(Z^2)/(2B) (device float, nullable), dZ = Z/B. */
 int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, void* stream);
 
+/* Flux.Optimise.ADAM over a flat parameter / gradient buffer (replaces the per-parameter `update!(opt, p.data, p.grad)`
+ * loop of examples/networks/network_glow.jl:38-42): m, v are the caller's moment buffers (zero before the first step),
+ * beta1_pow_t = beta1^t, beta2_pow_t = beta2^t for this step t >= 1 (Flux keeps the same running products). */
+int inb_adam_update(long long n, float* params, const float* grads, float* m, float* v, float lr, float beta1, float beta2,
+                    float eps, float beta1_pow_t, float beta2_pow_t, void* stream);
+
 /* ------------------------------------------------------------------ accounting (bench / tests)
  * inb_launch_count: kernels launched by this library since load (process wide).
  * Profiling: when enabled every kernel family is timed with CUDA events on the launching stream

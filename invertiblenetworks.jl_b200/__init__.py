@@ -8,14 +8,14 @@ it with ctypes; glow.py mirrors the reference's Julia API on torch CUDA tensors.
 from . import lib
 from . import dp
 from .lib import InbError, PRECISIONS
-from .glow import (ActNorm, Conv1x1, CouplingLayerGlow, NetworkConditionalGlow, NetworkGlow, NetworkGlow3D,
+from .glow import (ADAM, ActNorm, Conv1x1, CouplingLayerGlow, NetworkConditionalGlow, NetworkGlow, NetworkGlow3D,
                    Parameter, ResidualBlock, clear_grad, get_grads, get_params, nll_grad, set_params, squeeze,
                    unsqueeze)
 
 ConditionalLayerGlow = CouplingLayerGlow  # same class with n_cond > 0 (conditional_layer_glow.jl:61-66)
 
 __all__ = [
-    "ActNorm", "Conv1x1", "CouplingLayerGlow", "ConditionalLayerGlow", "NetworkConditionalGlow", "NetworkGlow",
+    "ADAM", "ActNorm", "Conv1x1", "CouplingLayerGlow", "ConditionalLayerGlow", "NetworkConditionalGlow", "NetworkGlow",
     "NetworkGlow3D", "Parameter", "ResidualBlock", "clear_grad", "get_grads", "get_params", "nll_grad",
     "set_params", "squeeze", "unsqueeze", "InbError", "PRECISIONS", "lib", "dp",
 ]

@@ -944,4 +944,15 @@ int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, voi
   });
 }
 
+int inb_adam_update(long long n, float* params, const float* grads, float* m, float* v, float lr, float beta1, float beta2,
+                    float eps, float beta1_pow_t, float beta2_pow_t, void* stream) {
+  return guarded([&] {
+    INB_CHECK(params && grads && m && v && n > 0, "bad argument");
+    INB_CHECK(beta1_pow_t < 1.f && beta2_pow_t < 1.f, "beta^t must be < 1 (t >= 1)");
+    Arena none;
+    Ctx c{(cudaStream_t)stream, &none, 0};
+    op_adam(c, n, params, grads, m, v, lr, beta1, beta2, eps, beta1_pow_t, beta2_pow_t);
+  });
+}
+
 }  // extern "C"

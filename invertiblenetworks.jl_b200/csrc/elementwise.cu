@@ -874,6 +874,27 @@ void op_nll_grad(Ctx& c, long long n, int B, const float* z, float* dz, double* 
   if (acc && loss) k_ld_finish<<<1, 1, 0, c.st>>>(acc, loss);
   INB_CUDA(cudaGetLastError());
 }
+// Flux.Optimise.ADAM over a flat buffer (the `update!(opt, p.data, p.grad)` loop of examples/networks/network_glow.jl:38-42
+// for all parameters in one launch):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+// x -= lr * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps)
+__global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       long long n, float lr, float b1, float b2, float eps, float c1, float c2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    x[i] -= lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+  }
+}
+void op_adam(Ctx& c, long long n, float* x, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,
+             float b1t, float b2t) {
+  if (c.dry()) return;
+  Prof pf(c, F_MISC, 1, 0, 28.0 * n);
+  k_adam<<<grid_for(n, 256, 4), 256, 0, c.st>>>(x, g, m, v, n, lr, b1, b2, eps, 1.f / (1.f - b1t), 1.f / (1.f - b2t));
+  INB_CUDA(cudaGetLastError());
+}
 void op_ld_finish(Ctx& c, const double* acc, float* out) {
   if (c.dry()) return;
   Prof pf(c, F_MISC, 1, 0, 0);

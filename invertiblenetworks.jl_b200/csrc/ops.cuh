@@ -49,6 +49,8 @@ void op_relu_grad(Ctx& c, long long n, const float* dy, const float* y, float* o
 void op_channel_sum(Ctx& c, long long px, int B, int C, const float* in, float* out);
 void op_nll_grad(Ctx& c, long long n, int B, const float* z, float* dz, double* acc, float* loss);
 void op_ld_finish(Ctx& c, const double* acc, float* out);
+void op_adam(Ctx& c, long long n, float* x, const float* g, float* m, float* v, float lr, float b1, float b2, float eps,
+             float b1t, float b2t);
 
 // ---------------------------------------------------------------- conv_simt.cu (INB_PREC_FP32)
 enum { PACK_CONV = 0, PACK_DATA = 1 };

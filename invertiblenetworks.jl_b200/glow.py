@@ -591,3 +591,22 @@ def nll_grad(Z: Tensor, batch: int):
     loss = torch.empty(1, device=Z.device)
     _l.call("inb_nll_grad", Z.numel(), batch, _l.ptr(Z), _l.ptr(dZ), _l.ptr(loss), _l.stream())
     return loss[0], dZ
+
+
+class ADAM:
+    """Flux.Optimise.ADAM(eta, (beta1, beta2)) applied to the flat parameter buffer of a network in one launch:
+    `opt = ADAM(G); ...; G.backward(dZ, Z); opt.step()` replaces the loop `for p in get_params(G):
+    update!(opt, p.data, p.grad)` of examples/networks/network_glow.jl:38-42 (480 launches for cfg2)."""
+
+    def __init__(self, G, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.G, self.lr, self.betas, self.eps = G, float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.m = torch.zeros_like(G.flat_params)
+        self.v = torch.zeros_like(G.flat_params)
+        self.t = 0
+
+    def step(self):
+        G = self.G
+        self.t += 1
+        b1, b2 = self.betas
+        _l.call("inb_adam_update", G.flat_params.numel(), _l.ptr(G.flat_params), _l.ptr(G.flat_grads), _l.ptr(self.m),
+                _l.ptr(self.v), self.lr, b1, b2, self.eps, b1 ** self.t, b2 ** self.t, _l.stream())

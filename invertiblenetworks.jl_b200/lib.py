@@ -63,6 +63,7 @@ SIGNATURES = {
     "inb_squeeze": (I, [I, I, I, I, I, I, P, P, P]),
     "inb_unsqueeze": (I, [I, I, I, I, I, I, P, P, P]),
     "inb_nll_grad": (I, [LL, I, P, P, P, P]),
+    "inb_adam_update": (I, [LL, P, P, P, P, F, F, F, F, F, F, P]),
     "inb_launch_count": (LL, []),
     "inb_prof_enable": (I, [I]),
     "inb_debug_chain_trace": (I, [P]),

@@ -236,4 +236,15 @@ function InvertibleNetworks.squeeze(X::CuArray{Float32,N}; pattern="column") whe
     return Y
 end
 
+# Optional replacement of the `for p in get_params(G); update!(opt, p.data, p.grad); end` loop with Flux.ADAM
+# (examples/networks/network_glow.jl:38-42) for callers that keep parameters and gradients in flat CuArrays:
+# one launch instead of 10*L*K.  m, v start at zero; t is the 1-based step count.
+function adam_update!(θ::CuArray{Float32}, ∇θ::CuArray{Float32}, m::CuArray{Float32}, v::CuArray{Float32};
+                      η=1f-3, β=(0.9f0, 0.999f0), ϵ=1f-8, t::Int=1)
+    check(ccall((:inb_adam_update, LIB), Cint,
+                (Clonglong, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Ptr{Cvoid}),
+                length(θ), dptr(θ), dptr(∇θ), dptr(m), dptr(v), η, β[1], β[2], ϵ, β[1]^t, β[2]^t, stream()))
+    return θ
+end
+
 end # module

@@ -173,3 +173,29 @@ def test_full_size_properties_cfg2_one_sample_pair():
     dX, Xr = G.backward(Z / 2, Z)
     assert rel(Xr, X) < 1e-5 and torch.isfinite(dX).all()
     assert sum(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in G.get_params()) == 60
+
+
+def test_adam_matches_flux_update_rule():
+    """inb_adam_update over the flat parameter buffer == Flux.Optimise.ADAM applied parameter by parameter
+    (examples/networks/network_glow.jl:38-42); restated in float64 for the check, three steps."""
+    torch.manual_seed(0)
+    G = inb200.NetworkGlow(2, 8, 2, 2, split_scales=True, device=DEV)
+    X = torch.rand(4, 2, 16, 16)
+    opt = inb200.ADAM(G, lr=1e-2)
+    x = None
+    m = v = None
+    b1, b2, eps, lr = 0.9, 0.999, 1e-8, 1e-2
+    for t in range(1, 4):
+        Z, ld = G.forward(g(X))
+        nll, dZ = inb200.nll_grad(Z, X.shape[0])
+        G.backward(dZ, Z)
+        gr = G.flat_grads.double().cpu()
+        if x is None:
+            x = G.flat_params.double().cpu()
+            m, v = torch.zeros_like(x), torch.zeros_like(x)
+        m = b1 * m + (1 - b1) * gr
+        v = b2 * v + (1 - b2) * gr * gr
+        x = x - lr * (m / (1 - b1 ** t)) / (torch.sqrt(v / (1 - b2 ** t)) + eps)
+        opt.step()
+        inb200.clear_grad(G)
+        assert rel(G.flat_params, x) < 1e-6, t
