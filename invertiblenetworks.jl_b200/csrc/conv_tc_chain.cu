@@ -1192,6 +1192,74 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     const uint32_t hready_leader = mapa_u32(smem_u32(hready), 0);
     uint32_t tl = 0;
     uint32_t cs = 0;  // chunk stores issued so far (store mode): slot cs % 2, use cs / 2
+    // qsum, second half of E3 (deferred): horizontal tap sums of tile `ptile` from the raw rows in shared memory into the
+    // dense Q tile, then its TMA store.  It touches no tensor memory, so it runs while the epilogue warps would otherwise
+    // wait for the tail of GEMM2's first half of the NEXT tile.
+    float* const raw = reinterpret_cast<float*>(pstag);
+    const int rp = a.n3pad + 4;  // row pitch in floats: 16-byte accesses of consecutive rows hit distinct banks
+    float* const qst = raw + 128 * rp;  // dense [128][nq], the box of the (unswizzled) TMA store
+    int qpending = -1;
+    auto qsum_finish = [&](int ptile) {
+      // items (pixel r, tap row tg, 4-channel group g), decoded with shifts and one multiply (W is a power of two,
+      // tg = rest / ngrp through a 16-bit reciprocal): nothing is kept in registers across tiles
+      const int nstep = rp + a.Cn;  // neighbour row, neighbour tap
+      const int ngrp = a.cq >> 2, items = 128 * a.ntg * ngrp;
+      const uint32_t inv = 65536u / (uint32_t)ngrp + 1u;
+      const int vmode = ((a.Cn & 3) == 0) ? 4 : (((a.Cn & 1) == 0) ? 2 : 1);
+#pragma unroll 1
+      for (int i = tid; i < items; i += EPI) {
+        const int r = i & 127, rest = i >> 7;
+        const int tg = (int)(((uint32_t)rest * inv) >> 16), g = rest - tg * ngrp;
+        const int x = r & (a.W - 1);
+        const bool left = x > 0, right = x + 1 < a.W;
+        const float* ctr = raw + r * rp + (tg * 3 + 1) * a.Cn + 4 * g;  // centre tap of this item's tap row
+        float4 acc;
+        if (vmode == 4) {
+          acc = *reinterpret_cast<const float4*>(ctr);
+          if (left) {
+            const float4 v = *reinterpret_cast<const float4*>(ctr - nstep);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+          if (right) {
+            const float4 v = *reinterpret_cast<const float4*>(ctr + nstep);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        } else if (vmode == 2) {
+          const bool hi2 = 4 * g + 2 < a.Cn;
+          float2 a0 = *reinterpret_cast<const float2*>(ctr);
+          float2 a1 = hi2 ? *reinterpret_cast<const float2*>(ctr + 2) : make_float2(0.f, 0.f);
+          if (left) {
+            const float2 v0 = *reinterpret_cast<const float2*>(ctr - nstep);
+            a0.x += v0.x; a0.y += v0.y;
+            if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr - nstep + 2); a1.x += v1.x; a1.y += v1.y; }
+          }
+          if (right) {
+            const float2 v0 = *reinterpret_cast<const float2*>(ctr + nstep);
+            a0.x += v0.x; a0.y += v0.y;
+            if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr + nstep + 2); a1.x += v1.x; a1.y += v1.y; }
+          }
+          acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+        } else {
+          float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            if ((dxi == 0 && !left) || (dxi == 2 && !right)) continue;
+            const float* src = ctr + (dxi - 1) * nstep;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (4 * g + u < a.Cn) t4[u] += src[u];
+          }
+          acc = make_float4(t4[0], t4[1], t4[2], t4[3]);
+        }
+        *reinterpret_cast<float4*>(qst + r * a.nq + tg * a.cq + 4 * g) = acc;
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+      if (tid == 0) {
+        tma_store_2d(&maps.P, qst, 0, ptile * 128);
+        bulk_commit();
+      }
+    };
     for (int tp = pair0; tp < npairs; tp += pstride, ++tl) {
       const int tile = 2 * tp + (int)rank;
       const uint32_t R0 = tmem + (tl & 1) * 256, R1 = tmem + ((tl & 1) ^ 1) * 256;
@@ -1271,6 +1339,10 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           mA = mB;
         }
         if (tr) tr[2 * stg + 1] = clock64();
+        if (stg == 0 && qpending >= 0) {
+          qsum_finish(qpending);
+          qpending = -1;
+        }
       }
       // E3: tap-expanded columns (region R0, <= 256 of them) -> P staging -> TMA store of P
       mbar_wait(d3f, tl & 1);
@@ -1280,13 +1352,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         // D3 rows -> plain fp32 rows in shared memory; then every (pixel, tap row, 4 channels) item adds its three
         // horizontal taps: Q[(y', x)][tg][n] = sum_dx D3[(y', x + dx)][(3 tg + dx + 1) Cn + n] (x + dx inside the image
         // row; a tile is whole image rows because 128 % W == 0); col2im then only sums over tap rows
-        float* raw = reinterpret_cast<float*>(pstag);
-        const int rp = a.n3pad + 4;  // row pitch in floats: 16-byte accesses of consecutive rows hit distinct banks
-        float* qst = raw + 128 * rp;  // dense [128][nq], the box of the (unswizzled) TMA store
-        long long* tq = (TRACE && tr && tl == 2) ? a.trace + 256 : nullptr;  // fine-grained E3 timeline of one thread
-        if (tq) tq[0] = clock64();
         if (tl > 0 && tid == 0) bulk_wait_read0();  // the previous tile's Pq store has read qst
-        if (tq) tq[1] = clock64();
         {
           const int c0 = 32 * kk;
           float* dst = raw + row * rp + c0;
@@ -1306,73 +1372,9 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
               *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           }
         }
-        if (tq) tq[2] = clock64();
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
-        if (tq) tq[3] = clock64();
-        // items (pixel r, tap row tg, 4-channel group g), decoded with shifts and one multiply (W is a power of two,
-        // tg = rest / ngrp through a 16-bit reciprocal): nothing is kept in registers across tiles
-        const int nstep = rp + a.Cn;  // neighbour row, neighbour tap
-        const int ngrp = a.cq >> 2, items = 128 * a.ntg * ngrp;
-        const uint32_t inv = 65536u / (uint32_t)ngrp + 1u;
-        const int vmode = ((a.Cn & 3) == 0) ? 4 : (((a.Cn & 1) == 0) ? 2 : 1);
-#pragma unroll 1
-        for (int i = tid; i < items; i += EPI) {
-          const int r = i & 127, rest = i >> 7;
-          const int tg = (int)(((uint32_t)rest * inv) >> 16), g = rest - tg * ngrp;
-          const int x = r & (a.W - 1);
-          const bool left = x > 0, right = x + 1 < a.W;
-          const float* ctr = raw + r * rp + (tg * 3 + 1) * a.Cn + 4 * g;  // centre tap of this item's tap row
-          float4 acc;
-          if (vmode == 4) {
-            acc = *reinterpret_cast<const float4*>(ctr);
-            if (left) {
-              const float4 v = *reinterpret_cast<const float4*>(ctr - nstep);
-              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            if (right) {
-              const float4 v = *reinterpret_cast<const float4*>(ctr + nstep);
-              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-          } else if (vmode == 2) {
-            const bool hi2 = 4 * g + 2 < a.Cn;
-            float2 a0 = *reinterpret_cast<const float2*>(ctr);
-            float2 a1 = hi2 ? *reinterpret_cast<const float2*>(ctr + 2) : make_float2(0.f, 0.f);
-            if (left) {
-              const float2 v0 = *reinterpret_cast<const float2*>(ctr - nstep);
-              a0.x += v0.x; a0.y += v0.y;
-              if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr - nstep + 2); a1.x += v1.x; a1.y += v1.y; }
-            }
-            if (right) {
-              const float2 v0 = *reinterpret_cast<const float2*>(ctr + nstep);
-              a0.x += v0.x; a0.y += v0.y;
-              if (hi2) { const float2 v1 = *reinterpret_cast<const float2*>(ctr + nstep + 2); a1.x += v1.x; a1.y += v1.y; }
-            }
-            acc = make_float4(a0.x, a0.y, a1.x, a1.y);
-          } else {
-            float t4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int dxi = 0; dxi < 3; ++dxi) {
-              if ((dxi == 0 && !left) || (dxi == 2 && !right)) continue;
-              const float* src = ctr + (dxi - 1) * nstep;
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (4 * g + u < a.Cn) t4[u] += src[u];
-            }
-            acc = make_float4(t4[0], t4[1], t4[2], t4[3]);
-          }
-          *reinterpret_cast<float4*>(qst + r * a.nq + tg * a.cq + 4 * g) = acc;
-        }
-        if (tq) tq[4] = clock64();
-        fence_proxy_async();
-        if (tq) tq[5] = clock64();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
-        if (tq) tq[6] = clock64();
-        if (tid == 0) {
-          tma_store_2d(&maps.P, qst, 0, tile * 128);
-          bulk_commit();
-        }
-        if (tq) tq[7] = clock64();
+        qpending = tile;  // the tap sums and the store run after E1 of the next tile (see qsum_finish)
       } else
 #pragma unroll 1
       for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
@@ -1414,6 +1416,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       }
       if (tr) tr[5] = clock64();
     }
+    if (qpending >= 0) qsum_finish(qpending);
     if (tid == 0) bulk_wait0();
   } else if (a.store) {
     // ------------------------------------------------------------ TMA store warp: hidden chunks -> HBM
