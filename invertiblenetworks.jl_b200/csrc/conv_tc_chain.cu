@@ -49,6 +49,7 @@ struct ChainArgs {
   // taps*Cn to (taps/3)*cq columns per pixel (Pq[m][tg*cq + n], cq = Cn rounded up to 4, pitch nq = (taps/3)*cq)
   int qsum, Cn, cq, nq, ntg;
   int pstag_bytes;        // k_rb_chain2: size of the P staging area
+  int npiece, n3piece;    // k_rb_chain2: GEMM3 runs in npiece passes of n3piece (<= 256) columns through the same TMEM region
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
@@ -957,6 +958,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   uint64_t* hready = d3f + 1;     // [4]  (leader's copy is the live one)
   uint64_t* sready = hready + 4;  // [2]
   uint64_t* sfree = sready + 2;   // [2]
+  uint64_t* e3free = sfree + 2;   // [1]  the epilogues have read a GEMM3 piece out of tensor memory (leader's copy)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 48);  // 48 barrier slots -> 384 bytes
   float* sbias = reinterpret_cast<float*>(tslot + 4);        // [2][256]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -966,7 +968,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   const int pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
   const int nhh = a.nh >> 1;          // columns of one half of D1 / D2
   const int qrows = a.nh >> 2;        // weight rows of one half held by this CTA
-  const int n3half = a.n3pad >> 1;    // weight rows of GEMM3 held by this CTA
+  const int n3half = a.n3piece >> 1;  // weight rows of a GEMM3 piece held by this CTA
   const int chalf = a.nchunk >> 1;    // chunks per column half
   const bool w3_one = NP * n3half * 128 <= (int)kPlane;  // a GEMM3 weight block (hi + lo) fits one ring granule
 
@@ -982,6 +984,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(d1h + s, 1); mbar_init(d2h + s, 1); }
       mbar_init(d3f, 1);
+      mbar_init(e3free, 2 * kEpi2Warps);
       for (int s = 0; s < 4; ++s) mbar_init(hready + s, 2 * kEpi2Warps);
       for (int s = 0; s < kChain2Slots; ++s) { mbar_init(sready + s, kEpi2Warps); mbar_init(sfree + s, 1); }
       fence_barrier_init();
@@ -1048,17 +1051,19 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
               tma_load_2d_cg2(&maps.W2[pl], bar, st + pl * qrows * 128, c * 64, h * nhh + (int)rank * qrows);
           }
         }
-        for (int c = 0; c < a.nchunk; ++c) {
-          if (w3_one) {  // both planes of the block fit one granule
-            uint8_t* st = acquire(NP * n3half * 128, bar);
+        for (int pc = 0; pc < a.npiece; ++pc) {
+          const int w3row = pc * a.n3piece + (int)rank * n3half;
+          for (int c = 0; c < a.nchunk; ++c) {
+            if (w3_one) {  // both planes of the block fit one granule
+              uint8_t* st = acquire(NP * n3half * 128, bar);
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl)
-              tma_load_2d_cg2(&maps.W3[pl], bar, st + pl * n3half * 128, c * 64, (int)rank * n3half);
-          } else {
+              for (int pl = 0; pl < NP; ++pl) tma_load_2d_cg2(&maps.W3[pl], bar, st + pl * n3half * 128, c * 64, w3row);
+            } else {
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              uint8_t* st = acquire(n3half * 128, bar);
-              tma_load_2d_cg2(&maps.W3[pl], bar, st, c * 64, (int)rank * n3half);
+              for (int pl = 0; pl < NP; ++pl) {
+                uint8_t* st = acquire(n3half * 128, bar);
+                tma_load_2d_cg2(&maps.W3[pl], bar, st, c * 64, w3row);
+              }
             }
           }
         }
@@ -1068,7 +1073,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, both tiles of the pair)
     if (leader && elect_one()) {
       const uint32_t idesc_12 = make_idesc_bf16(256, nhh, 0, 0);   // GEMM1 / GEMM2 run one column half at a time
-      const uint32_t idesc_3 = make_idesc_bf16(256, a.n3pad, 0, 0);
+      const uint32_t idesc_3 = make_idesc_bf16(256, a.n3piece, 0, 0);
       const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
       uint32_t it = 0, tl = 0;
       long long twait = 0;
@@ -1115,7 +1120,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         long long* tr = (TRACE && a.trace && blockIdx.x == 0 && tl < 16) ? a.trace + tl * 16 : nullptr;
         if (tr) tr[0] = clock64();
         if (tl > 0) {  // R0 held the A operand of the previous pair's GEMM3: let those MMAs retire first
-          mbar_wait(d3f, (tl - 1) & 1);
+          mbar_wait(d3f, (tl * a.npiece - 1) & 1);
           tc_fence_after();
         }
         // GEMM1: both column halves per im2col block (the block stays resident while its two weight halves pass)
@@ -1158,9 +1163,16 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         }
         if (tr) { tr[3] = clock64(); tr[13] = twait; }
         twait = 0;
-        for (int c = 0; c < a.nchunk; ++c) {
-          mbar_wait(hready + c, 1);
+        for (int pc = 0; pc < a.npiece; ++pc) {
+        if (pc > 0) {  // the epilogues of both CTAs have read the previous piece out of R0
+          mbar_wait(e3free, (tl * (a.npiece - 1) + pc - 1) & 1);
           tc_fence_after();
+        }
+        for (int c = 0; c < a.nchunk; ++c) {
+          if (pc == 0) {
+            mbar_wait(hready + c, 1);
+            tc_fence_after();
+          }
           if (tr && c == 0) tr[4] = clock64();
           const uint32_t bH = stage_wait();
           const int slotH = it % a.stages;
@@ -1177,6 +1189,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           if (NT == 3 && !w3_one) umma2_commit_mc(empty + slotL);
         }
         umma2_commit_mc(d3f);
+        }
         if (tr) { tr[5] = clock64(); tr[14] = twait; }
         twait = 0;
       }
@@ -1190,6 +1203,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const int tid = e * 32 + lane;
     const uint32_t hready_leader = mapa_u32(smem_u32(hready), 0);
+    const uint32_t e3free_leader = mapa_u32(smem_u32(e3free), 0);
     uint32_t tl = 0;
     uint32_t cs = 0;  // chunk stores issued so far (store mode): slot cs % 2, use cs / 2
     // qsum, second half of E3 (deferred): horizontal tap sums of tile `ptile` from the raw rows in shared memory into the
@@ -1344,8 +1358,9 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           qpending = -1;
         }
       }
-      // E3: tap-expanded columns (region R0, <= 256 of them) -> P staging -> TMA store of P
-      mbar_wait(d3f, tl & 1);
+      // E3: tap-expanded columns (region R0, <= 256 of them per piece) -> P staging -> TMA store of P
+      for (int pc = 0; pc < a.npiece; ++pc) {
+      mbar_wait(d3f, (tl * a.npiece + pc) & 1);
       tc_fence_after();
       if (tr) tr[4] = clock64();
       if (a.qsum) {
@@ -1377,10 +1392,10 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         qpending = tile;  // the tap sums and the store run after E1 of the next tile (see qsum_finish)
       } else
 #pragma unroll 1
-      for (int slab = 0; slab * 128 < a.n3pad; ++slab) {
-        const int ncols = min(128, a.n3pad - slab * 128);
+      for (int slab = 0; slab * 128 < a.n3piece; ++slab) {
+        const int ncols = min(128, a.n3piece - slab * 128);
         const uint32_t dsrc = R0 + slab * 128 + lane_sel;
-        if (slab > 0 || tl > 0) {  // the previous P stores have read the staging area (long ago when slab == 0)
+        if (slab > 0 || tl > 0 || pc > 0) {  // the previous P stores have read the staging area
           if (tid == 0) bulk_wait_read0();
           asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
         }
@@ -1410,9 +1425,16 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
         if (tid == 0) {
-          for (int g = 0; g * 32 < ncols; ++g) tma_store_2d(&maps.P, pstag + g * kPlane, slab * 128 + g * 32, tile * 128);
+          for (int g = 0; g * 32 < ncols; ++g)
+            tma_store_2d(&maps.P, pstag + g * kPlane, pc * a.n3piece + slab * 128 + g * 32, tile * 128);
           bulk_commit();
         }
+      }
+      if (pc + 1 < a.npiece) {  // R0 may take the next piece (all of this warp's TMEM loads have completed)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(e3free_leader);
+      }
       }
       if (tr) tr[5] = clock64();
     }
@@ -1582,7 +1604,12 @@ static long long* g_chain_trace = nullptr;
 static int g_chain_trace_launch = 0;  // successive launches write successive 32 x 16 blocks (4 of them, cyclic)
 void chain_set_trace(long long* p) { g_chain_trace = p; g_chain_trace_launch = 0; }
 
-int chain_n3pad(int taps, int Cn) { return (taps * Cn + 15) / 16 * 16; }
+// columns of the tap-expanded GEMM: a multiple of 16; beyond 256 a multiple of 32, so that the CTA-pair kernel can run
+// it as two equal passes of a multiple of 16 columns
+int chain_n3pad(int taps, int Cn) {
+  const int n = (taps * Cn + 15) / 16 * 16;
+  return n <= 256 ? n : (n + 31) / 32 * 32;
+}
 
 int chain_kpad(int taps, int C, int extra) { return (taps * C + extra + 63) / 64 * 64; }
 
@@ -1635,7 +1662,9 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     if (!e) e = getenv("INB_CHAIN_SMEM") && getenv("INB_CHAIN_SMEM")[0] == '1' ? "smem" : "";
     return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
   }();
-  const bool pair = a.n3pad <= 256 && force == 0;
+  const bool pair = (a.n3pad <= 256 || (a.n3pad <= 512 && a.n3pad % 32 == 0)) && force == 0;
+  a.npiece = a.n3pad <= 256 ? 1 : 2;
+  a.n3piece = a.n3pad / a.npiece;
   static const bool no_qsum = [] { const char* e = getenv("INB_CHAIN_QSUM"); return e && e[0] == '0'; }();
   a.Cn = s.Cn;
   a.cq = (s.Cn + 3) / 4 * 4;
@@ -1654,7 +1683,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.stages = stages;
   const size_t smem = fixed + stages * (pair ? (size_t)kPlane : stage) + aux;
   ChainMaps mp{};
-  const int wrows = pair ? s.nh / 4 : 128, w3rows = pair ? a.n3pad / 2 : 128;
+  const int wrows = pair ? s.nh / 4 : 128, w3rows = pair ? a.n3piece / 2 : 128;
   for (int pl = 0; pl < 2; ++pl) {
     mp.A[pl] = make_rows_map(pl ? s.in.lo : s.in.hi, s.in.pitch, a.M, 64, 128);
     mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, wrows);
