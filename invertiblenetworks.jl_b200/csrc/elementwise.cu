@@ -368,7 +368,8 @@ k_hh_an_bwd(const float* __restrict__ dy, long long dybs, const float* __restric
   for (int i = 0; i < RI; ++i)
 #pragma unroll
     for (int j = 0; j < RJ; ++j) gacc[i][j] = 0.f;
-  float sacc = 0.f, bacc = 0.f;  // threads < C: ds, db of channel tid
+  constexpr int NG = BWD_T / C;   // threads per channel in the ds / db walk
+  float sacc = 0.f, bacc = 0.f;   // threads < C * NG: partial ds * s, db of channel tid % C
 
   const long long ntiles = (total + BWD_T - 1) / BWD_T;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -445,17 +446,20 @@ k_hh_an_bwd(const float* __restrict__ dy, long long dybs, const float* __restric
           }
       }
     }
-    if (s && dsdb && tid < C) {
-      const float sc = sm.s[tid], bc = sm.b[tid];
+    if (s && dsdb && tid < C * NG) {
+      // sum_p dA (A - b) / s = (sum_p dA A - b sum_p dA) / s: the division leaves the loop, and the walk over the tile is
+      // split over NG = 128 / C threads per channel (C threads alone made this the longest phase of a tile)
+      const int ch = tid % C, j = tid / C;
+      const float bc = sm.b[ch];
       float s1 = 0.f, b1 = 0.f;
-      for (int p = 0; p < BWD_T; p += 4) {
-        float4 av = *reinterpret_cast<const float4*>(As + tid * BWD_LD + p);
-        float4 ev = *reinterpret_cast<const float4*>(Es + tid * BWD_LD + p);
+      for (int p = 4 * j; p < BWD_T; p += 4 * NG) {
+        float4 av = *reinterpret_cast<const float4*>(As + ch * BWD_LD + p);
+        float4 ev = *reinterpret_cast<const float4*>(Es + ch * BWD_LD + p);
         // dead pixels carry dA = 0, so they add nothing
-        s1 = fmaf(ev.x, (av.x - bc) / sc, s1);
-        s1 = fmaf(ev.y, (av.y - bc) / sc, s1);
-        s1 = fmaf(ev.z, (av.z - bc) / sc, s1);
-        s1 = fmaf(ev.w, (av.w - bc) / sc, s1);
+        s1 = fmaf(ev.x, av.x - bc, s1);
+        s1 = fmaf(ev.y, av.y - bc, s1);
+        s1 = fmaf(ev.z, av.z - bc, s1);
+        s1 = fmaf(ev.w, av.w - bc, s1);
         b1 += (ev.x + ev.y) + (ev.z + ev.w);
       }
       sacc += s1;
@@ -472,9 +476,20 @@ k_hh_an_bwd(const float* __restrict__ dy, long long dybs, const float* __restric
         if (r < C && cc < C) atomicAdd(gram + r * C + cc, (double)gacc[i][j]);
       }
   }
-  if (s && dsdb && tid < C) {
-    atomicAdd(dsdb + tid, (double)sacc);
-    atomicAdd(dsdb + C + tid, (double)bacc);
+  if (s && dsdb) {
+    // the NG partial sums of a channel meet in shared memory (the A tile is free now), one pair of atomics per channel
+    __syncthreads();
+    if (tid < C * NG) {
+      As[tid] = sacc;
+      As[C * NG + tid] = bacc;
+    }
+    __syncthreads();
+    if (tid < C) {
+      float u = 0.f, w = 0.f;
+      for (int j = 0; j < NG; ++j) { u += As[j * C + tid]; w += As[C * NG + j * C + tid]; }
+      atomicAdd(dsdb + tid, (double)(u / sm.s[tid]));
+      atomicAdd(dsdb + C + tid, (double)w);
+    }
   }
 }
 
