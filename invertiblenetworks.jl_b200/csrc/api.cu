@@ -132,6 +132,7 @@ struct inb_plan {
   uint32_t graph_hist[3] = {0, 0, 0};
   long long graph_captures = 0, graph_replays = 0, graph_direct = 0;
   cudaStream_t capture_stream = nullptr;
+  SideLane lane;
 };
 
 static int an_index(const inb_plan* p, int i, int j, int which) { return 2 * (i * p->d.K + j) + which; }
@@ -407,6 +408,7 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
                       gr ? gr[anc_index(p, 1)] : nullptr);
     c.ar->release(m2);
   }
+  if (c.lane) c.lane->join(c.st);  // the gradient kernels on the side lane belong to this call
   c.ar->release(m);
 }
 
@@ -444,7 +446,26 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
     p->persist = p->ar.off;
   }
   p->ar.off = p->persist;
-  return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
+  static const bool no_lane = [] { const char* e = getenv("INB_SIDE_LANE"); return e && e[0] == '0'; }();
+  if (!p->lane.st && !no_lane) {  // side lane: stream, L*K + 2 events, one Gram block per flow step
+    const int steps = p->d.L * p->d.K;
+    int cmax = 1;
+    for (const ScaleInfo& s : p->sc) cmax = std::max(cmax, s.C);
+    p->lane.nev = steps + 2;
+    p->lane.ev = new cudaEvent_t[p->lane.nev];
+    for (int i = 0; i < p->lane.nev; ++i) INB_CUDA(cudaEventCreateWithFlags(&p->lane.ev[i], cudaEventDisableTiming));
+    p->lane.pool_bytes = (size_t)steps * ((((size_t)cmax * cmax + 2 * cmax) * sizeof(double) + 255) & ~size_t(255));
+    INB_CUDA(cudaMalloc(&p->lane.pool, p->lane.pool_bytes));
+    INB_CUDA(cudaStreamCreateWithFlags(&p->lane.st, cudaStreamNonBlocking));
+  }
+  Ctx c{(cudaStream_t)stream, &p->ar, p->d.precision};
+  if (p->lane.st) {
+    p->lane.next = 0;
+    p->lane.pool_off = 0;
+    p->lane.used = false;
+    c.lane = &p->lane;
+  }
+  return c;
 }
 
 // ---------------------------------------------------------------- CUDA-graph replay of whole-network calls
@@ -586,6 +607,10 @@ int inb_glow_plan_destroy(inb_plan* p) {
       for (auto& g : slot)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+    if (p->lane.st) cudaStreamDestroy(p->lane.st);
+    for (int i = 0; i < p->lane.nev; ++i) cudaEventDestroy(p->lane.ev[i]);
+    delete[] p->lane.ev;
+    if (p->lane.pool) cudaFree(p->lane.pool);
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;
   });

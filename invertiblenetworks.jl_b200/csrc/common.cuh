@@ -80,10 +80,45 @@ struct Arena {
   void release(size_t m) { off = m; }
 };
 
+// A second stream for small kernels nothing later in the same call waits for (the closed-form Householder / ActNorm
+// gradient kernels: one CTA, fp64, ~15 us each, 96 of them per cfg2 backward).  fork() makes the lane wait for the
+// work enqueued so far on the main stream, join() makes the main stream wait for the lane; inside a graph capture both
+// become edges of the graph.  What such kernels read lives in `pool`, which is not recycled within a call.
+struct SideLane {
+  cudaStream_t st = nullptr;
+  cudaEvent_t* ev = nullptr;
+  int nev = 0, next = 0;
+  char* pool = nullptr;
+  size_t pool_bytes = 0, pool_off = 0;
+  bool used = false;
+  void* take(size_t n) {
+    size_t a = (pool_off + 255) & ~size_t(255);
+    if (!pool || a + n > pool_bytes || next + 2 > nev) return nullptr;
+    pool_off = a + n;
+    return pool + a;
+  }
+  void fork(cudaStream_t main) {
+    INB_CUDA(cudaEventRecord(ev[next], main));
+    INB_CUDA(cudaStreamWaitEvent(st, ev[next], 0));
+    ++next;
+    used = true;
+  }
+  void join(cudaStream_t main) {
+    if (used) {
+      INB_CUDA(cudaEventRecord(ev[next], st));
+      INB_CUDA(cudaStreamWaitEvent(main, ev[next], 0));
+    }
+    used = false;
+    next = 0;
+    pool_off = 0;
+  }
+};
+
 struct Ctx {
   cudaStream_t st;
   Arena* ar;
   int prec;  // INB_PREC_*
+  SideLane* lane = nullptr;
   bool dry() const { return ar->dry; }
 };
 

@@ -381,7 +381,14 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
   h.Y2 = c.ar->f32(rb_hidden_elems(rs));
   h.G = c.ar->f32(rb_hidden_elems(rs));
   float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
-  double* gram = c.ar->f64((size_t)C * C + 2 * C);
+  // Gram matrix + ActNorm sums: from the side lane's pool when there is one (their consumers run on the lane)
+  double* gram = nullptr;
+  bool on_lane = false;
+  if (c.lane && !c.dry()) {
+    gram = reinterpret_cast<double*>(c.lane->take(((size_t)C * C + 2 * C) * sizeof(double)));
+    on_lane = gram != nullptr;
+  }
+  if (!gram) gram = c.ar->f64((size_t)C * C + 2 * C);
   double* dsdb = gram + (size_t)C * C;
   op_zero(c, gram, ((size_t)C * C + 2 * C) * sizeof(double));
   View y2 = sub(y, C1, px), dy2 = sub(dy, C1, px);
@@ -394,8 +401,13 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
   rb_backward(c, rs, Y3, y2, cond, p.rb, h, g.rb, dy2, dy2.p, dy2.bs, dcond);
   // Conv1x1 inverse on (dX_, X_) + ActNorm backward              glow.jl:159, actnorm.jl:100-123
   op_hh_an_bwd(c, px, f.B, C, dy, y, dx, x, p.s, p.b, p.v1, p.v2, p.v3, gram, p.s ? dsdb : nullptr);
-  op_hh_grad_finish(c, C, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3);
-  if (p.s) op_an_grad_finish(c, C, px, dsdb, p.s, f.logdet, g.s, g.b);
+  Ctx fc = c;
+  if (on_lane) {
+    c.lane->fork(c.st);
+    fc.st = c.lane->st;
+  }
+  op_hh_grad_finish(fc, C, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3);
+  if (p.s) op_an_grad_finish(fc, C, px, dsdb, p.s, f.logdet, g.s, g.b);
   c.ar->release(m);
 }
 
