@@ -385,11 +385,13 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sb = 1 if args.config == "cfg2" else gb
-        v, sec = time_oracle(cfg, sb, 1, 0 if args.config == "cfg2" else 1, threads)
+        sb = 2 if args.config == "cfg2" else gb
+        nst = 4 if args.config == "cfg2" else 20
+        v, sec = time_oracle(cfg, sb, nst, 0 if args.config == "cfg2" else 1, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"1 step of batch {sb} of the full {args.config} network on the host "
-                                          f"cores (torch-CPU oracle, {threads} threads)"}
+                                "sample": f"{nst} steps of batch {sb} of the full {args.config} network on the host "
+                                          f"cores (torch-CPU oracle restating the Julia reference, {threads} threads, "
+                                          f"{sec * nst:.1f} s)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
