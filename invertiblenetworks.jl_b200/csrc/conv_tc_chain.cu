@@ -1284,13 +1284,19 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       for (int stg = 0; stg < 2; ++stg) {
         const uint32_t reg = (stg ? R1 : R0) + lane_sel + 16 * kk;
         const float* sb = sbias + stg * 256 + 16 * kk;
-        const long long hrow = m * (a.nh >> 4) + kk;  // 16-bit word 4c + kk of the row's bit plane
+        // this kernel's bit-plane layout: the 16-bit words of a row are ordered [kk][c], so the nchunk words a thread
+        // produces (or needs) in a stage are contiguous: ONE 8-byte store (load) per thread and stage.  (Per-chunk 2-byte
+        // stores were 32 L1 transactions per warp and chunk and cost ~290 cycles per chunk.)
+        const long long hrow = m * (a.nh >> 4) + kk * a.nchunk;
         const uint16_t* mk = reinterpret_cast<const uint16_t*>(stg ? a.mask2 : a.mask1) + hrow;
         uint16_t* bo = reinterpret_cast<uint16_t*>(stg ? a.bits2 : a.bits1) + hrow;
+        unsigned long long macc = 0, bacc = 0;  // masks of the stage's chunks (16 bits each): read / produced
 
         uint64_t* dh = stg ? d2h : d1h;
-        uint32_t mA = 0, mB = 0;
-        if (a.mode == 1) mA = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk) : 0u;  // chunk 0's mask, before the wait
+        if (a.mode == 1 && live && !(a.exp & 2)) {  // all of the stage's masks, before the wait
+          if (a.nchunk == 4) macc = __ldg(reinterpret_cast<const unsigned long long*>(mk));
+          else macc = __ldg(reinterpret_cast<const uint32_t*>(mk));
+        }
         mbar_wait(dh + 0, tl & 1);
         tc_fence_after();
         if (tr) tr[2 * stg] = clock64();
@@ -1315,13 +1321,14 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           // in place: the 16 fp32 columns just read become 8 packed hi + 8 packed lo columns
           tmem_st8(reg + 64 * c, wh);
           if (NT == 3) tmem_st8(reg + 64 * c + 8, wl);
-          if (a.mode == 0 && a.store && live) bo[4 * c] = (uint16_t)bits;
+          if (a.mode == 0 && a.store) bacc |= (unsigned long long)(bits & 0xFFFFu) << (16 * c);
           int slot = 0;
           if (a.store) {
             slot = (int)(cs % kChain2Slots);
             const uint32_t use = cs / kChain2Slots;
             if (use > 0) mbar_wait(sfree + slot, (use - 1) & 1);  // the slot's previous TMA store has read it
             uint8_t* dst = stag + slot * SLOT + row * 128;
+            if (!(a.exp & 8))
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const uint32_t off = (uint32_t)(((kk * 2 + g) ^ (row & 7)) << 4);
@@ -1329,7 +1336,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
               if (NT == 3)
                 *reinterpret_cast<uint4*>(dst + kPlane + off) = make_uint4(wl[4 * g], wl[4 * g + 1], wl[4 * g + 2], wl[4 * g + 3]);
             }
-            fence_proxy_async();
+            if (!(a.exp & 16)) fence_proxy_async();
             ++cs;
           }
           tmem_st_wait();
@@ -1347,10 +1354,12 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             tc_fence_after();
           }
           tmem_ld16(reg + 64 * c, rA);
-          if (a.mode == 1 && c + 1 < a.nchunk) mB = (live && !(a.exp & 2)) ? (uint32_t)__ldg(mk + 4 * (c + 1)) : 0u;
           tmem_ld_wait();
-          emit(c, rA, mA);
-          mA = mB;
+          emit(c, rA, (uint32_t)(macc >> (16 * c)) & 0xFFFFu);
+        }
+        if (a.mode == 0 && a.store && live) {
+          if (a.nchunk == 4) *reinterpret_cast<unsigned long long*>(bo) = bacc;
+          else *reinterpret_cast<uint32_t*>(bo) = (uint32_t)bacc;
         }
         if (tr) tr[2 * stg + 1] = clock64();
         if (stg == 0 && qpending >= 0) {
@@ -1450,9 +1459,11 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           for (int c = 0; c < a.nchunk; ++c, ++cs) {
             const int slot = (int)(cs % kChain2Slots);
             mbar_wait(sready + slot, (cs / kChain2Slots) & 1);
+            if (!(a.exp & 4)) {
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl)
-              tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+              for (int pl = 0; pl < NP; ++pl)
+                tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+            }
             bulk_commit();
             if (cs > 0) {  // one store stays in flight; the one before it has read its slot
               bulk_wait_read1();
