@@ -1553,6 +1553,47 @@ __global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
   }
 }
 
+// thread = (pixel, group of 4 channels), G = ceil(Cn / 4) threads per pixel: the G float4 loads of a pixel's tap (row)
+// are adjacent lanes, so a warp instruction touches ~11 pixels x G chunks = a third of the cache lines the
+// thread-per-pixel walk does (that one is L1-transaction bound: 32 lines per instruction).  Needs 16-byte aligned
+// groups: cstride and the pitch multiples of 4 (always true for the tap-row sums Pq).
+template <int G>
+__global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
+  const long long m = (long long)blockIdx.x * 32 + threadIdx.x / G;
+  const int g = threadIdx.x % G;
+  if (m >= a.M) return;
+  const long long b = m / a.px, pix = m - b * a.px;
+  long long t = pix;
+  const int x = (int)(t % a.W); t /= a.W;
+  const int y = (int)(t % a.H); t /= a.H;
+  const int z = (int)t;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tap = 0; tap < a.taps; ++tap) {
+    int dx, dy, dz;
+    if (a.qsum) { dx = 0; dy = tap % 3 - 1; dz = (a.D > 1) ? tap / 3 - 1 : 0; }
+    else chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
+    const int xx = x + dx, yy = y + dy, zz = z + dz;
+    if (xx < 0 || xx >= a.W || yy < 0 || yy >= a.H || zz < 0 || zz >= a.D) continue;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(
+        a.P + (m + dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.cstride + 4 * g));
+    acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+  }
+  const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = 4 * g + j;
+    if (n >= a.Cn) break;
+    float v = v4[j];
+    if (a.add && n < a.add_n) v += a.add[b * a.add_bs + (long long)n * a.px + pix];
+    if (n < a.n0) {
+      a.out0[b * a.out0_bs + (long long)n * a.px + pix] = v;
+    } else {
+      float* qq = a.out1 + b * a.out1_bs + (long long)(n - a.n0) * a.px + pix;
+      *qq = a.out1_accum ? (*qq + v) : v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- weight packing for one chain pass
 // One launch packs the three operands of a pass into bf16 hi/lo planes:
 //   w1 [nh][kp]     dense-K rows against the im2col operand:  column tap*C1 + c  <-  wa[n][c][T-1-tap]   (NNlib conv)
@@ -1769,7 +1810,16 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     const unsigned nb = (unsigned)cdiv(a.M, 128);
     const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;
     const bool v2 = s.Cn % 2 == 0 && ca.cstride % 2 == 0 && ca.n3pad % 2 == 0;
-    if (v4) k_col2im<4><<<nb, 128, 0, c.st>>>(ca);
+    // 16-byte groups: the tap-row sums are padded to 4 channels per tap row; the full P needs Cn % 4 == 0
+    const bool g4 = ca.cstride % 4 == 0 && ca.n3pad % 4 == 0 && (a.qsum || s.Cn % 4 == 0);
+    const int G = (s.Cn + 3) / 4;
+    const unsigned nbg = (unsigned)cdiv(a.M, 32);
+    static const bool no_g = [] { const char* e = getenv("INB_COL2IM_G"); return e && e[0] == '0'; }();
+    if (g4 && !no_g && G == 2) k_col2im_g<2><<<nbg, 64, 0, c.st>>>(ca);
+    else if (g4 && !no_g && G == 3) k_col2im_g<3><<<nbg, 96, 0, c.st>>>(ca);
+    else if (g4 && !no_g && G == 6) k_col2im_g<6><<<nbg, 192, 0, c.st>>>(ca);
+    else if (g4 && !no_g && G == 12) k_col2im_g<12><<<nbg, 384, 0, c.st>>>(ca);
+    else if (v4) k_col2im<4><<<nb, 128, 0, c.st>>>(ca);
     else if (v2) k_col2im<2><<<nb, 128, 0, c.st>>>(ca);
     else k_col2im<1><<<nb, 128, 0, c.st>>>(ca);
     INB_CUDA(cudaGetLastError());
