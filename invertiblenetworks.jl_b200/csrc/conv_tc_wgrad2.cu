@@ -192,38 +192,52 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p]; fixed summation order (eight
-// interleaved partial sums per output keep eight loads in flight: the kernel is a latency-bound column walk)
-__global__ void k_wgrad_reduce(const float* __restrict__ part, int ncta, int np, int pitch, int qtot, int C, int T,
-                               float* __restrict__ dw, const float* __restrict__ dbpart, float* __restrict__ db) {
+// dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p] in a fixed order: four lanes share an
+// output (each walks every fourth partial with two interleaved sums, then two shuffles) - the kernel is a latency-bound
+// column walk, so the parallelism is what counts; consecutive outputs stay on consecutive lane groups (coalesced)
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, int ncta, int np, int pitch, int qtot,
+                                                      int C, int T, float* __restrict__ dw,
+                                                      const float* __restrict__ dbpart, float* __restrict__ db) {
   const int ncol = T * C;
-  const long long total = (long long)np * ncol;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total + (dbpart ? np : 0);
-       i += (long long)gridDim.x * blockDim.x) {
-    if (i >= total) {
-      const int p = (int)(i - total);
-      float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int k = 0;
-      for (; k + 8 <= ncta; k += 8)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s8[u] += dbpart[(long long)(k + u) * np + p];
-      for (; k < ncta; ++k) s8[0] += dbpart[(long long)k * np + p];
-      db[p] = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
-      continue;
+  const long long total = (long long)np * ncol, outs = total + (dbpart ? np : 0);
+  const int sub = threadIdx.x >> 6;  // which quarter of the partials (a warp works on 32 consecutive outputs)
+  const int ol = threadIdx.x & 63;
+  __shared__ float sm[4][64];
+  for (long long i0 = (long long)blockIdx.x * 64; i0 < outs; i0 += (long long)gridDim.x * 64) {
+    const long long i = i0 + ol;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < outs) {
+      const float* src;
+      long long step;
+      if (i >= total) {
+        src = dbpart + (i - total);
+        step = np;
+      } else {
+        const int col = (int)(i % ncol), p = (int)(i / ncol);
+        const int g = col >> 8, cg = col & 255;
+        src = part + ((long long)g * ncta * np + p) * pitch + cg;
+        step = (long long)np * pitch;
+      }
+      int k = sub;
+      for (; k + 4 < ncta; k += 8) {
+        s0 += __ldg(src + k * step);
+        s1 += __ldg(src + (k + 4) * step);
+      }
+      if (k < ncta) s0 += __ldg(src + k * step);
     }
-    const int col = (int)(i % ncol), p = (int)(i / ncol);
-    const int g = col >> 8, cg = col & 255;
-    const float* src = part + ((long long)g * ncta * np + p) * pitch + cg;
-    const long long stride = (long long)np * pitch;
-    float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int k = 0;
-    for (; k + 8 <= ncta; k += 8)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) s8[u] += __ldg(src + (k + u) * stride);
-    for (; k < ncta; ++k) s8[0] += __ldg(src + k * stride);
-    const float s = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
-    const int tap = col / C, cc = col - tap * C;
-    dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
+    sm[sub][ol] = s0 + s1;
+    __syncthreads();
+    if (sub == 0 && i < outs) {
+      const float s = (sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol]);
+      if (i >= total) {
+        db[i - total] = s;
+      } else {
+        const int col = (int)(i % ncol), p = (int)(i / ncol);
+        const int tap = col / C, cc = col - tap * C;
+        dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
+      }
+    }
+    __syncthreads();
   }
   (void)qtot;
 }
@@ -280,7 +294,7 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   }
   INB_CUDA(cudaGetLastError());
   const long long outs = (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
-  k_wgrad_reduce<<<(unsigned)std::min<long long>(cdiv(outs, 256), 148 * 8), 256, 0, c.st>>>(
+  k_wgrad_reduce<<<(unsigned)std::min<long long>(cdiv(outs, 64), 148 * 8), 256, 0, c.st>>>(
       part, (int)gx, s.np, nqmax, a.qtot, s.C, s.T, s.dw, a.dbpart, s.db);
   INB_CUDA(cudaGetLastError());
   c.ar->release(mk);
