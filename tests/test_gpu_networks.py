@@ -199,3 +199,25 @@ def test_adam_matches_flux_update_rule():
         opt.step()
         inb200.clear_grad(G)
         assert rel(G.flat_params, x) < 1e-6, t
+
+
+def test_cuda_matches_golden():
+    """The CUDA path against the committed oracle vectors (tests/golden/glow_small.npz): forward, logdet, dX and every
+    gradient of a small NetworkGlow, float32 tolerance."""
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glow_small.npz"))
+    n_in, nh, L, K = [int(v) for v in gold["glow_cfg"]]
+    G = inb200.NetworkGlow(n_in, nh, L, K, split_scales=True, device=DEV)
+    nparam = sum(1 for k in gold.files if k.startswith("glow_p"))
+    inb200.set_params(G, [torch.from_numpy(gold[f"glow_p{i:03d}"]) for i in range(nparam)])
+    X = torch.from_numpy(gold["glow_X"])
+    Z, ld = G.forward(g(X))
+    assert rel(Z, torch.from_numpy(gold["glow_Z"])) < TOL_OUT
+    assert abs(ld.item() - float(gold["glow_logdet"])) < TOL_LOGDET * abs(float(gold["glow_logdet"])) + 1e-4
+    dZ = Z / X.shape[0]
+    dX, Xr = G.backward(dZ, Z)
+    assert rel(Xr, X) < 1e-5
+    assert rel(dX, torch.from_numpy(gold["glow_dX"])) < 10 * TOL_OUT
+    for i, p in enumerate(G.get_params()):
+        assert rel(p.grad, torch.from_numpy(gold[f"glow_g{i:03d}"])) < 10 * TOL_GRAD, i

@@ -303,3 +303,28 @@ def test_param_order_and_counts():
     step0 = P[8:16]
     assert [tuple(p.data.shape) for p in step0] == [(4,), (4,), (4,), (32, 2, 3, 3), (32, 32, 1, 1),
                                                     (32, 4, 3, 3), (32,), (32,)]
+
+
+def test_oracle_matches_golden():
+    """The committed vectors (tests/golden/make_golden.py: float64 oracle on seeded inputs) pin the oracle against
+    drift: any edit of the restatement that changes its numbers shows up here.  They are oracle-generated, not
+    reference-generated (the oracle itself stays 'parity unpinned', see oracle/glow_oracle.py)."""
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glow_small.npz"))
+    n_in, nh, L, K = [int(v) for v in gold["glow_cfg"]]
+    G = O.NetworkGlow(n_in, nh, L, K, split_scales=True, seed=5, dtype=torch.float64, faithful=False)
+    ps = G.get_params()
+    for i, p in enumerate(ps):
+        p.data = torch.from_numpy(gold[f"glow_p{i:03d}"]).double()
+    X = torch.from_numpy(gold["glow_X"]).double()
+    Z, ld = G.forward(X)
+    dX, Xr = G.backward(Z / X.shape[0], Z)
+    r = lambda a, b: float(torch.linalg.norm(a.reshape(-1) - torch.from_numpy(b).double().reshape(-1)) /
+                           max(torch.linalg.norm(torch.from_numpy(b).double().reshape(-1)), 1e-300))
+    assert r(Z, gold["glow_Z"]) < 1e-12
+    assert abs(float(ld) - float(gold["glow_logdet"])) < 1e-10 * abs(float(gold["glow_logdet"]))
+    assert r(dX, gold["glow_dX"]) < 1e-11
+    assert r(Xr, gold["glow_X"]) < 1e-6   # float32 input recovered by inversion
+    for i, p in enumerate(ps):
+        assert r(p.grad, gold[f"glow_g{i:03d}"]) < 1e-10, i
