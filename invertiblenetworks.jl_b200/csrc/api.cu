@@ -3,6 +3,7 @@
 #include "../../include/inb200.h"
 #include "glow.cuh"
 #include <mutex>
+#include <vector>
 
 #include <cstring>
 #include <memory>
@@ -272,14 +273,25 @@ static void drive_forward(inb_plan* p, Ctx& c, int B, const float* X, const floa
       cchan = s.Ccond;
     }
     FlowShape f = flow_shape(p, i, B);
+    // the chain operands of the scale's K blocks are packed in one launch before the first step
+    size_t mpack = c.ar->mark();
+    std::vector<PackedW> packs(d.K);
+    bool prepacked = false;
+    {  // also in the sizing pass (no parameters there): the planes must be counted
+      std::vector<RBParams> rbp(d.K);
+      for (int j = 0; j < d.K; ++j) rbp[j] = flow_params(p, i, j, prm).rb;
+      prepacked = rb_prepack_chain(c, f.rb(), rbp.data(), d.K, 0, packs.data());
+    }
     for (int j = 0; j < d.K; ++j) {
       FlowParams fp = flow_params(p, i, j, prm);
+      if (prepacked) fp.rb.pre[0] = &packs[j];
       if (init) op_actnorm_init(c, s.g.px, B, s.C, cur, const_cast<float*>(fp.s), const_cast<float*>(fp.b));
       View out = view(buf[which], (long long)s.C * s.g.px);
       flow_forward(c, f, cur, out, cond, fp, p->ld);  // :116-118
       cur = out;
       which ^= 1;
     }
+    c.ar->release(mpack);
     if (s.has_split) {  // :120-124: X = first part, Z = second part
       long long off = z_offset(p, B, i);
       int zc = s.C - s.kc;
@@ -352,8 +364,19 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
         op_copy(c, s.g.px, B, zc, view(const_cast<float*>(dZ) + off, (long long)zc * s.g.px), sub(dy, s.kc, s.g.px));
     }
     FlowShape f = flow_shape(p, i, B);
+    size_t mpack = c.ar->mark();
+    std::vector<PackedW> packs_f(d.K), packs_b(d.K);
+    bool pre_f = false, pre_b = false;
+    {
+      std::vector<RBParams> rbp(d.K);
+      for (int j = 0; j < d.K; ++j) rbp[j] = flow_params(p, i, j, prm).rb;
+      pre_f = rb_prepack_chain(c, f.rb(), rbp.data(), d.K, 0, packs_f.data());
+      if (grads) pre_b = rb_prepack_chain(c, f.rb(), rbp.data(), d.K, 1, packs_b.data());
+    }
     for (int j = d.K - 1; j >= 0; --j) {
       FlowParams fp = flow_params(p, i, j, prm);
+      if (pre_f) fp.rb.pre[0] = &packs_f[j];
+      if (pre_b) fp.rb.pre[1] = &packs_b[j];
       View xo = y, dxo = dy;
       const bool final_step = (i == 0 && j == 0 && !d.split_scales);
       if (final_step) {  // write straight into the caller's buffers
@@ -367,6 +390,7 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
         flow_inverse(c, f, y, xo, cond, fp);  // :139-140
       }
     }
+    c.ar->release(mpack);
     if (d.split_scales) {  // :186-187 unsqueeze
       Geo gout = (i == 0) ? p->g0 : make_geo(d.ndims, s.g.W * 2, s.g.H * 2, s.g.D * 2);
       int cout = s.C >> d.ndims;

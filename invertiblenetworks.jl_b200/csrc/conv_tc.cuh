@@ -114,6 +114,14 @@ bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int 
 // the three packed operands of one chain pass in a single launch (conv_tc_chain.cu: k_pack_chain_tc)
 void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
                       int n3pad, const float* wc, Planes w1, Planes w2, Planes w3);
+// the same packing for several blocks of one shape in ONE launch (the K flow steps of a scale: their weights do not
+// change during a network-level call, so all of them are packed before the first step runs)
+struct PackChainItem {
+  const float *wa, *wb, *wc;
+  Planes w1, w2, w3;
+};
+void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int Cn, int n3pad, const PackChainItem* items,
+                         int n);
 void op_rb_chain(Ctx& c, const ChainSpec& s);
 void chain_set_trace(long long* p);
 

@@ -1641,6 +1641,71 @@ __global__ void k_pack_chain_tc(const PackChainArgs a) {
     dl[o] = l;
   }
 }
+constexpr int kPackMulti = 24;
+struct PackMultiArgs {
+  int nh, T, C1, kp, Cn, n3pad, w2_data, n, blocks_per_item;
+  const float* wa[kPackMulti];
+  const float* wb[kPackMulti];
+  const float* wc[kPackMulti];
+  __nv_bfloat16* dst[kPackMulti][6];  // w1h, w1l, w2h, w2l, w3h, w3l
+};
+__global__ void k_pack_chain_multi(const __grid_constant__ PackMultiArgs a) {
+  const int item = blockIdx.x / a.blocks_per_item, lb = blockIdx.x - item * a.blocks_per_item;
+  const float *wa = a.wa[item], *wb = a.wb[item], *wc = a.wc[item];
+  const long long n1 = (long long)a.nh * a.kp, n2 = (long long)a.nh * a.nh, n3 = (long long)a.n3pad * a.nh;
+  for (long long i = lb * (long long)blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += (long long)a.blocks_per_item * blockDim.x) {
+    float v = 0.f;
+    int which;
+    long long o;
+    if (i < n1) {
+      o = i;
+      const int k = (int)(i % a.kp), n = (int)(i / a.kp);
+      if (k < a.T * a.C1) {
+        const int tap = k / a.C1, cc = k - tap * a.C1;
+        v = wa[((long long)n * a.C1 + cc) * a.T + (a.T - 1 - tap)];
+      }
+      which = 0;
+    } else if (i < n1 + n2) {
+      o = i - n1;
+      const int cc = (int)(o % a.nh), n = (int)(o / a.nh);
+      v = a.w2_data ? wb[(long long)cc * a.nh + n] : wb[(long long)n * a.nh + cc];
+      if (n == cc) v += 1.f;
+      which = 2;
+    } else {
+      o = i - n1 - n2;
+      const int c = (int)(o % a.nh), r = (int)(o / a.nh);
+      if (r < a.T * a.Cn) {
+        const int tap = r / a.Cn, n = r - tap * a.Cn;
+        v = wc[((long long)c * a.Cn + n) * a.T + tap];
+      }
+      which = 4;
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    a.dst[item][which][o] = h;
+    a.dst[item][which + 1][o] = l;
+  }
+}
+void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int Cn, int n3pad, const PackChainItem* items,
+                         int n) {
+  if (c.dry()) return;
+  const long long per = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
+  for (int i0 = 0; i0 < n; i0 += kPackMulti) {
+    PackMultiArgs a{};
+    a.nh = nh; a.T = T; a.C1 = C1; a.kp = kp; a.Cn = Cn; a.n3pad = n3pad; a.w2_data = w2_data;
+    a.n = std::min(kPackMulti, n - i0);
+    a.blocks_per_item = (int)std::min<long long>(cdiv(per, 256), 64);
+    for (int j = 0; j < a.n; ++j) {
+      const PackChainItem& it = items[i0 + j];
+      a.wa[j] = it.wa; a.wb[j] = it.wb; a.wc[j] = it.wc;
+      a.dst[j][0] = it.w1.hi; a.dst[j][1] = it.w1.lo; a.dst[j][2] = it.w2.hi; a.dst[j][3] = it.w2.lo;
+      a.dst[j][4] = it.w3.hi; a.dst[j][5] = it.w3.lo;
+    }
+    Prof pf(c, F_PACK, 1, 0, 8.0 * per * a.n);
+    k_pack_chain_multi<<<(unsigned)(a.n * a.blocks_per_item), 256, 0, c.st>>>(a);
+    INB_CUDA(cudaGetLastError());
+  }
+}
 void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
                       int n3pad, const float* wc, Planes w1, Planes w2, Planes w3) {
   if (c.dry()) return;

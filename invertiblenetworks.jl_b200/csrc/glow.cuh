@@ -17,8 +17,13 @@ struct RBShape {
   int T1() const { return k1 == 1 ? 1 : (g.nd == 3 ? 27 : 9); }
   int T2() const { return k2 == 1 ? 1 : (g.nd == 3 ? 27 : 9); }
 };
+// chain operands of a block packed ahead of time (rb_prepack_chain): [0] the forward / recompute pass, [1] the backward pass
+struct PackedW {
+  Planes w1, w2, w3;
+};
 struct RBParams {
   const float *W1, *W2, *W3, *b1, *b2;
+  const PackedW* pre[2] = {nullptr, nullptr};
 };
 struct RBGrads {
   float *W1, *W2, *W3, *b1, *b2;
@@ -63,6 +68,10 @@ struct FlowGrads {
   RBGrads rb;
 };
 size_t rb_hidden_elems(const RBShape& s);
+// Packs the chain operands of n blocks of shape s (direction 0: forward / recompute, 1: backward) into planes taken
+// from the caller's arena scope, one launch per 24 blocks; returns false (and packs nothing) when the blocks do not run
+// on the fused chain.  The caller points RBParams::pre[direction] at out[i].
+bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int direction, PackedW* out);
 
 // ActNorm -> CouplingLayerGlow forward: x -> y (y != x)
 void flow_forward(Ctx& c, const FlowShape& f, View x, View y, View cond, const FlowParams& p, double* ld);

@@ -1,6 +1,7 @@
 // layers.cu - ResidualBlock and flow-step (ActNorm -> Conv1x1 -> affine coupling) compositions.
 #include "glow.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace inb {
 
@@ -162,6 +163,25 @@ static bool rb_chain_ok(const RBShape& s) {
   return chain_supported(s.g, s.B, s.k1, s.k2, s.nh, s.Cin(), s.Cout) &&
          chain_supported(s.g, s.B, s.k1, s.k2, s.nh, s.Cout, s.Cin());
 }
+bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int direction, PackedW* out) {
+  if (c.prec == 0 || !rb_chain_ok(s) || n <= 0) return false;
+  const int T1 = s.T1(), nh = s.nh;
+  const int C1 = direction == 0 ? s.Cin() : s.Cout, Cn = direction == 0 ? s.Cout : s.Cin();
+  const int kp = chain_kpad(T1, C1, 0), n3pad = chain_n3pad(T1, Cn);
+  std::vector<PackChainItem> items(n);
+  for (int i = 0; i < n; ++i) {
+    out[i].w1 = planes_new(c, nh, kp);
+    out[i].w2 = planes_new(c, nh, nh);
+    out[i].w3 = planes_new(c, n3pad, nh);
+    items[i].wa = direction == 0 ? prm[i].W1 : prm[i].W3;
+    items[i].wb = prm[i].W2;
+    items[i].wc = direction == 0 ? prm[i].W3 : prm[i].W1;
+    items[i].w1 = out[i].w1; items[i].w2 = out[i].w2; items[i].w3 = out[i].w3;
+  }
+  op_pack_chain_multi(c, nh, T1, C1, kp, direction, Cn, n3pad, items.data(), n);
+  return true;
+}
+
 static ConvTcSpec tc_base(const RBShape& s) {
   ConvTcSpec cs{};
   cs.g = s.g;
@@ -189,9 +209,14 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     size_t m = c.ar->mark();
     Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
     const int n3pad = chain_n3pad(T1, s.Cout);
-    Planes W1 = planes_new(c, nh, kp), W2 = planes_new(c, nh, nh), W3 = planes_new(c, n3pad, nh);
-    // conv(X, W1) | W2 + I (the skip of :125) | \nabla conv_data(., W3) tap-expanded
-    op_pack_chain_tc(c, nh, T1, Cin, kp, p.W1, p.W2, 0, s.Cout, n3pad, p.W3, W1, W2, W3);
+    Planes W1, W2, W3;
+    if (p.pre[0]) {  // packed by rb_prepack_chain before the scale's first flow step
+      W1 = p.pre[0]->w1; W2 = p.pre[0]->w2; W3 = p.pre[0]->w3;
+    } else {
+      W1 = planes_new(c, nh, kp); W2 = planes_new(c, nh, nh); W3 = planes_new(c, n3pad, nh);
+      // conv(X, W1) | W2 + I (the skip of :125) | \nabla conv_data(., W3) tap-expanded
+      op_pack_chain_tc(c, nh, T1, Cin, kp, p.W1, p.W2, 0, s.Cout, n3pad, p.W3, W1, W2, W3);
+    }
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
@@ -249,11 +274,16 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     Planes G1 = planes_new(c, M, nh);
     const int kp = chain_kpad(T1, Cout, 0);
     const int n3pad = chain_n3pad(T1, Cin);
-    Planes W3c = planes_new(c, nh, kp), W2d = planes_new(c, nh, nh), W1e = planes_new(c, n3pad, nh);
+    Planes W3c, W2d, W1e;
+    if (p.pre[1]) {
+      W3c = p.pre[1]->w1; W2d = p.pre[1]->w2; W1e = p.pre[1]->w3;
+    } else {
+      W3c = planes_new(c, nh, kp); W2d = planes_new(c, nh, nh); W1e = planes_new(c, n3pad, nh);
+    }
     Planes dcol = planes_new(c, M, kp);
     op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol);
     // conv(dY3, W3) :151 | \nabla conv_data(., W2) + I (the '+ dY2' of :155) | \nabla conv_data(., W1) tap-expanded :162
-    op_pack_chain_tc(c, nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
+    if (!p.pre[1]) op_pack_chain_tc(c, nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
     ChainSpec cs{};
     cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
     cs.in = dcol; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
