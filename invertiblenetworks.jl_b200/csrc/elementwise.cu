@@ -58,9 +58,10 @@ __device__ __forceinline__ double block_sum(double v) {
   return r;
 }
 
-// activation_functions.jl:160-162
+// activation_functions.jl:160-162: high / (1 + e^-x) + low / (1 + e^x) = low + (high - low) / (1 + e^-x), one
+// exponential and one division instead of two of each (the coupling kernels are ALU-bound, not HBM-bound)
 __device__ __forceinline__ float sigmoid_lh(float x, float low, float high) {
-  return high / (1.f + expf(-x)) + low / (1.f + expf(x));
+  return low + (high - low) / (1.f + expf(-x));
 }
 
 // ---------------------------------------------------------------- squeeze / unsqueeze / copy
@@ -696,27 +697,29 @@ void op_hh_an_bwd(Ctx& c, long long px, int B, int C, View dy, View y, View dx, 
 template <int V>
 __global__ void k_coupling_fwd(const float* __restrict__ x1, long long xbs, float* __restrict__ y1,
                                long long ybs, const float* __restrict__ rb, long long px, int C1,
-                               long long total, float low, float high, double* __restrict__ ld, float invB) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+                               float low, float high, double* __restrict__ ld, float invB) {
+  // grid (pixel vectors, channel, sample): no index divisions, a few vectors per thread
+  const int ch = blockIdx.y;
+  const long long b = blockIdx.z;
+  const long long pxv = px / V;
+  const float* xp = x1 + b * xbs + ch * px;
+  const float* lp = rb + (b * 2 * C1 + ch) * px;
+  const float* tp = rb + (b * 2 * C1 + C1 + ch) * px;
+  float* yp = y1 + b * ybs + ch * px;
   float lsum = 0.f;
-  if (g < total) {
-    const long long pxv = px / V;
-    long long t = g;
-    long long pv = t % pxv; t /= pxv;
-    int ch = (int)(t % C1);
-    long long b = t / C1;
-    long long pix = pv * V;
+  for (long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x; pv < pxv; pv += (long long)gridDim.x * blockDim.x) {
+    const long long pix = pv * V;
     float xv[V], ls[V], tv[V], out[V];
-    ldv<V>(x1 + b * xbs + ch * px + pix, xv);
-    ldv<V>(rb + (b * 2 * C1 + ch) * px + pix, ls);
-    ldv<V>(rb + (b * 2 * C1 + C1 + ch) * px + pix, tv);
+    ldv<V>(xp + pix, xv);
+    ldv<V>(lp + pix, ls);
+    ldv<V>(tp + pix, tv);
 #pragma unroll
     for (int u = 0; u < V; ++u) {
       float S = sigmoid_lh(fmaxf(ls[u], 0.f), low, high);  // RB output ReLU (layer_residual_block.jl:133)
       out[u] = S * xv[u] + fmaxf(tv[u], 0.f);              // glow.jl:112
       lsum += logf(fabsf(S));                              // glow.jl:210
     }
-    stv<V>(y1 + b * ybs + ch * px + pix, out);
+    stv<V>(yp + pix, out);
   }
   if (ld) {
     double r = block_sum((double)lsum);
@@ -727,69 +730,78 @@ __global__ void k_coupling_fwd(const float* __restrict__ x1, long long xbs, floa
 template <int V>
 __global__ void k_coupling_inv(const float* __restrict__ y1, long long ybs, float* __restrict__ x1,
                                long long xbs, const float* __restrict__ rb, long long px, int C1,
-                               long long total, float low, float high) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= total) return;
+                               float low, float high) {
+  const int ch = blockIdx.y;
+  const long long b = blockIdx.z;
   const long long pxv = px / V;
-  long long t = g;
-  long long pv = t % pxv; t /= pxv;
-  int ch = (int)(t % C1);
-  long long b = t / C1;
-  long long pix = pv * V;
-  float yv[V], ls[V], tv[V], out[V];
-  ldv<V>(y1 + b * ybs + ch * px + pix, yv);
-  ldv<V>(rb + (b * 2 * C1 + ch) * px + pix, ls);
-  ldv<V>(rb + (b * 2 * C1 + C1 + ch) * px + pix, tv);
+  const float* yp = y1 + b * ybs + ch * px;
+  const float* lp = rb + (b * 2 * C1 + ch) * px;
+  const float* tp = rb + (b * 2 * C1 + C1 + ch) * px;
+  float* xp = x1 + b * xbs + ch * px;
+  for (long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x; pv < pxv; pv += (long long)gridDim.x * blockDim.x) {
+    const long long pix = pv * V;
+    float yv[V], ls[V], tv[V], out[V];
+    ldv<V>(yp + pix, yv);
+    ldv<V>(lp + pix, ls);
+    ldv<V>(tp + pix, tv);
 #pragma unroll
-  for (int u = 0; u < V; ++u) {
-    float S = sigmoid_lh(fmaxf(ls[u], 0.f), low, high);
-    out[u] = (yv[u] - fmaxf(tv[u], 0.f)) / (S + 1.1920929e-07f);  // glow.jl:127, eps(Float32)
+    for (int u = 0; u < V; ++u) {
+      float S = sigmoid_lh(fmaxf(ls[u], 0.f), low, high);
+      out[u] = (yv[u] - fmaxf(tv[u], 0.f)) / (S + 1.1920929e-07f);  // glow.jl:127, eps(Float32)
+    }
+    stv<V>(xp + pix, out);
   }
-  stv<V>(x1 + b * xbs + ch * px + pix, out);
 }
 
 template <int V>
 __global__ void k_coupling_bwd(const float* __restrict__ y1, long long ybs, float* __restrict__ x1,
                                long long xbs, const float* __restrict__ dy1, long long dybs,
                                float* __restrict__ dx1, long long dxbs, float* __restrict__ rb,
-                               long long px, int C1, long long total, float low, float high, float invB) {
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= total) return;
+                               long long px, int C1, float low, float high, float invB) {
+  const int ch = blockIdx.y;
+  const long long b = blockIdx.z;
   const long long pxv = px / V;
-  long long t = g;
-  long long pv = t % pxv; t /= pxv;
-  int ch = (int)(t % C1);
-  long long b = t / C1;
-  long long pix = pv * V;
-  float yv[V], dyv[V], ls[V], tv[V], xo[V], dxo[V], gl[V], gt[V];
-  float* pls = rb + (b * 2 * C1 + ch) * px + pix;
-  float* ptv = rb + (b * 2 * C1 + C1 + ch) * px + pix;
-  ldv<V>(y1 + b * ybs + ch * px + pix, yv);
-  ldv<V>(dy1 + b * dybs + ch * px + pix, dyv);
-  ldv<V>(pls, ls);
-  ldv<V>(ptv, tv);
+  const float* yp = y1 + b * ybs + ch * px;
+  const float* dyp = dy1 + b * dybs + ch * px;
+  float* plsb = rb + (b * 2 * C1 + ch) * px;
+  float* ptvb = rb + (b * 2 * C1 + C1 + ch) * px;
+  float* xp = x1 + b * xbs + ch * px;
+  float* dxp = dx1 + b * dxbs + ch * px;
+  for (long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x; pv < pxv; pv += (long long)gridDim.x * blockDim.x) {
+    const long long pix = pv * V;
+    float yv[V], dyv[V], ls[V], tv[V], xo[V], dxo[V], gl[V], gt[V];
+    ldv<V>(yp + pix, yv);
+    ldv<V>(dyp + pix, dyv);
+    ldv<V>(plsb + pix, ls);
+    ldv<V>(ptvb + pix, tv);
 #pragma unroll
-  for (int u = 0; u < V; ++u) {
-    float S = sigmoid_lh(fmaxf(ls[u], 0.f), low, high);
-    float X1 = (yv[u] - fmaxf(tv[u], 0.f)) / (S + 1.1920929e-07f);  // glow.jl:127
-    float dS = dyv[u] * X1;                                         // glow.jl:144
-    dS -= invB / S;                                                 // glow.jl:145-147,211 (invB = 0 w/o logdet)
-    xo[u] = X1;
-    dxo[u] = dyv[u] * S;                                            // glow.jl:149
-    // activation_functions.jl:213-217: gradient from the output through the logit
-    float xx = logf(S - low) - logf(high - S);
-    float e = expf(-xx);
-    float dl = (high - low) * dS * e / ((1.f + e) * (1.f + e));
-    // _relugrad of the block's output ReLU (activation_functions.jl:84): pass when pre-activation >= 0
-    gl[u] = (ls[u] < 0.f) ? 0.f : dl;
-    gt[u] = (tv[u] < 0.f) ? 0.f : dyv[u];  // dT = dY1 (glow.jl:143)
+    for (int u = 0; u < V; ++u) {
+      float S = sigmoid_lh(fmaxf(ls[u], 0.f), low, high);
+      float X1 = (yv[u] - fmaxf(tv[u], 0.f)) / (S + 1.1920929e-07f);  // glow.jl:127
+      float dS = dyv[u] * X1;                                         // glow.jl:144
+      dS -= invB / S;                                                 // glow.jl:145-147,211 (invB = 0 w/o logdet)
+      xo[u] = X1;
+      dxo[u] = dyv[u] * S;                                            // glow.jl:149
+      // activation_functions.jl:213-217: gradient from the output through the logit x = log(S - low) - log(high - S);
+      // e^-x is the ratio itself, no logarithms needed
+      float e = (high - S) / (S - low);
+      float dl = (high - low) * dS * e / ((1.f + e) * (1.f + e));
+      // _relugrad of the block's output ReLU (activation_functions.jl:84): pass when pre-activation >= 0
+      gl[u] = (ls[u] < 0.f) ? 0.f : dl;
+      gt[u] = (tv[u] < 0.f) ? 0.f : dyv[u];  // dT = dY1 (glow.jl:143)
+    }
+    stv<V>(xp + pix, xo);
+    stv<V>(dxp + pix, dxo);
+    stv<V>(plsb + pix, gl);
+    stv<V>(ptvb + pix, gt);
   }
-  stv<V>(x1 + b * xbs + ch * px + pix, xo);
-  stv<V>(dx1 + b * dxbs + ch * px + pix, dxo);
-  stv<V>(pls, gl);
-  stv<V>(ptv, gt);
 }
 
+// grid of the coupling kernels: (pixel vectors / 512, channel, sample) - two vectors per thread on large planes
+static dim3 coupling_grid(long long pxv, int C1, int B) {
+  INB_CHECK(C1 <= 65535 && B <= 65535, "coupling: channel / batch count exceeds the grid limits");
+  return dim3((unsigned)std::max<long long>(1, cdiv(pxv, 512)), (unsigned)C1, (unsigned)B);
+}
 static int pick_vec_ew(long long px, std::initializer_list<const View*> vs, const float* rb) {
   int v = 4;
   while (v > 1) {
@@ -806,12 +818,11 @@ void op_coupling_fwd(Ctx& c, long long px, int B, int C1, View x1, View y1, cons
   if (c.dry()) return;
   Prof pf(c, F_COUPLING_FWD, 1, 0, 16.0 * B * C1 * px);
   int V = pick_vec_ew(px, {&x1, &y1}, rb);
-  long long total = px / V * C1 * B;
-  int grid = (int)cdiv(total, 256);
+  const dim3 grid = coupling_grid(px / V, C1, B);
   float invB = 1.f / (float)B;
-  if (V == 4) k_coupling_fwd<4><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, total, low, high, ld, invB);
-  else if (V == 2) k_coupling_fwd<2><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, total, low, high, ld, invB);
-  else k_coupling_fwd<1><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, total, low, high, ld, invB);
+  if (V == 4) k_coupling_fwd<4><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);
+  else if (V == 2) k_coupling_fwd<2><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);
+  else k_coupling_fwd<1><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);
   INB_CUDA(cudaGetLastError());
 }
 void op_coupling_inv(Ctx& c, long long px, int B, int C1, View y1, View x1, const float* rb, float low,
@@ -819,11 +830,10 @@ void op_coupling_inv(Ctx& c, long long px, int B, int C1, View y1, View x1, cons
   if (c.dry()) return;
   Prof pf(c, F_COUPLING_INV, 1, 0, 16.0 * B * C1 * px);
   int V = pick_vec_ew(px, {&x1, &y1}, rb);
-  long long total = px / V * C1 * B;
-  int grid = (int)cdiv(total, 256);
-  if (V == 4) k_coupling_inv<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, total, low, high);
-  else if (V == 2) k_coupling_inv<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, total, low, high);
-  else k_coupling_inv<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, total, low, high);
+  const dim3 grid = coupling_grid(px / V, C1, B);
+  if (V == 4) k_coupling_inv<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, low, high);
+  else if (V == 2) k_coupling_inv<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, low, high);
+  else k_coupling_inv<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, rb, px, C1, low, high);
   INB_CUDA(cudaGetLastError());
 }
 void op_coupling_bwd(Ctx& c, long long px, int B, int C1, View y1, View x1, View dy1, View dx1,
@@ -831,12 +841,11 @@ void op_coupling_bwd(Ctx& c, long long px, int B, int C1, View y1, View x1, View
   if (c.dry()) return;
   Prof pf(c, F_COUPLING_BWD, 1, 0, 32.0 * B * C1 * px);
   int V = pick_vec_ew(px, {&x1, &y1, &dy1, &dx1}, rb);
-  long long total = px / V * C1 * B;
-  int grid = (int)cdiv(total, 256);
+  const dim3 grid = coupling_grid(px / V, C1, B);
   float invB = logdet ? 1.f / (float)B : 0.f;
-  if (V == 4) k_coupling_bwd<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, total, low, high, invB);
-  else if (V == 2) k_coupling_bwd<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, total, low, high, invB);
-  else k_coupling_bwd<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, total, low, high, invB);
+  if (V == 4) k_coupling_bwd<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
+  else if (V == 2) k_coupling_bwd<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
+  else k_coupling_bwd<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
   INB_CUDA(cudaGetLastError());
 }
 
