@@ -1559,14 +1559,17 @@ __global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
 // groups: cstride and the pitch multiples of 4 (always true for the tap-row sums Pq).
 template <int G>
 __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
-  const long long m = (long long)blockIdx.x * 32 + threadIdx.x / G;
+  // grid (pixels of a sample / 32, sample): the pixel decode is 32-bit (the kernel is instruction-bound; the 64-bit
+  // divisions of a flat pixel index were most of its instructions)
+  const int pix = (int)(blockIdx.x * 32 + threadIdx.x / G);
   const int g = threadIdx.x % G;
-  if (m >= a.M) return;
-  const long long b = m / a.px, pix = m - b * a.px;
-  long long t = pix;
-  const int x = (int)(t % a.W); t /= a.W;
-  const int y = (int)(t % a.H); t /= a.H;
-  const int z = (int)t;
+  if (pix >= (int)a.px) return;
+  const long long b = blockIdx.y;
+  const long long m = b * a.px + pix;
+  const int x = pix % a.W;
+  const int yz = pix / a.W;
+  const int y = yz % a.H;
+  const int z = yz / a.H;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int tap = 0; tap < a.taps; ++tap) {
     int dx, dy, dz;
@@ -1876,9 +1879,11 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;
     const bool v2 = s.Cn % 2 == 0 && ca.cstride % 2 == 0 && ca.n3pad % 2 == 0;
     // 16-byte groups: the tap-row sums are padded to 4 channels per tap row; the full P needs Cn % 4 == 0
-    const bool g4 = ca.cstride % 4 == 0 && ca.n3pad % 4 == 0 && (a.qsum || s.Cn % 4 == 0);
+    const bool g4 = ca.cstride % 4 == 0 && ca.n3pad % 4 == 0 && (a.qsum || s.Cn % 4 == 0) && s.B <= 65535 &&
+                    s.g.px < (1ll << 31);
     const int G = (s.Cn + 3) / 4;
-    const unsigned nbg = (unsigned)cdiv(a.M, 32);
+    const dim3 nbg((unsigned)cdiv(s.g.px, 32), (unsigned)s.B, 1);
+
     static const bool no_g = [] { const char* e = getenv("INB_COL2IM_G"); return e && e[0] == '0'; }();
     if (g4 && !no_g && G == 2) k_col2im_g<2><<<nbg, 64, 0, c.st>>>(ca);
     else if (g4 && !no_g && G == 3) k_col2im_g<3><<<nbg, 96, 0, c.st>>>(ca);
