@@ -86,6 +86,7 @@ struct Wgrad2TcSpec {
   float* db;
 };
 void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
+void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n);  // one reduction launch for up to three gradients
 
 // Fused pass of the block's three contractions (conv_tc_chain.cu): im2col-GEMM -> per-pixel GEMM ->
 // tap-expanded GEMM + col2im.  mode 0 = forward (bias + ReLU epilogues), mode 1 = backward (relu-grad masks).

@@ -195,9 +195,21 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
 // dw[p][c][T-1-tap] = sum_cta part[g][cta][p][col], db[p] = sum_cta dbpart[cta][p] in a fixed order: four lanes share an
 // output (each walks every fourth partial with two interleaved sums, then two shuffles) - the kernel is a latency-bound
 // column walk, so the parallelism is what counts; consecutive outputs stay on consecutive lane groups (coalesced)
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, int ncta, int np, int pitch, int qtot,
-                                                      int C, int T, float* __restrict__ dw,
-                                                      const float* __restrict__ dbpart, float* __restrict__ db) {
+struct WgradReduceDesc {
+  const float* part;
+  int ncta, np, pitch, C, T;
+  float* dw;
+  const float* dbpart;
+  float* db;
+};
+struct WgradReduceArgs {
+  WgradReduceDesc d[3];
+};
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
+  const WgradReduceDesc& q = a.d[blockIdx.y];  // one weight gradient per grid row (the three of a block in one launch)
+  const float* __restrict__ part = q.part;
+  const float* __restrict__ dbpart = q.dbpart;
+  const int ncta = q.ncta, np = q.np, pitch = q.pitch, C = q.C, T = q.T;
   const int ncol = T * C;
   const long long total = (long long)np * ncol, outs = total + (dbpart ? np : 0);
   const int sub = threadIdx.x >> 6;  // which quarter of the partials (a warp works on 32 consecutive outputs)
@@ -230,19 +242,20 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
     if (sub == 0 && i < outs) {
       const float s = (sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol]);
       if (i >= total) {
-        db[i - total] = s;
+        q.db[i - total] = s;
       } else {
         const int col = (int)(i % ncol), p = (int)(i / ncol);
         const int tap = col / C, cc = col - tap * C;
-        dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
+        q.dw[((long long)p * C + cc) * T + (T - 1 - tap)] = s;
       }
     }
     __syncthreads();
   }
-  (void)qtot;
 }
 
-void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
+// launches the split-K kernel of one weight gradient; its partial tiles stay allocated (the caller releases the arena
+// scope after the reduction) and are described in `rd`; returns the number of outputs
+static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& rd) {
   INB_CHECK(s.np == 128 || s.np == 256, "tensor-core wgrad: np = %d must be 128 or 256", s.np);
   INB_CHECK(s.Q.pitch % 64 == 0 && s.P.pitch == s.np, "tensor-core wgrad: operand pitches must be multiples of 64");
   INB_CHECK(s.T * s.C <= s.Q.pitch, "tensor-core wgrad: Q has %d columns, need %d", s.Q.pitch, s.T * s.C);
@@ -272,18 +285,17 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
   a.blocks_per_cta = (int)cdiv(a.nblocks, ctas);
   const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);  // every CTA owns at least one block
   // scratch: partial tiles [ng][gx][np][nqmax] and partial bias sums [gx][np]
-  size_t mk = c.ar->mark();
   float* part = c.ar->f32((size_t)ng * gx * s.np * nqmax);
   float* dbpart = c.ar->f32((size_t)gx * s.np);  // sized in the dry run too (gradient pointers are fake there)
   a.dbpart = s.db ? dbpart : nullptr;
-  if (c.dry()) { c.ar->release(mk); return; }
+  if (c.dry()) return 0;
   const size_t smem = (size_t)stages * a.stage_bytes + 17 * 8 + 16;
   CUtensorMap mP0 = make_rows_map(s.P.hi, s.P.pitch, s.M, 64, kWgPB);
   CUtensorMap mP1 = make_rows_map(s.P.lo, s.P.pitch, s.M, 64, kWgPB);
   CUtensorMap mQ0 = make_rows_map(s.Q.hi, s.Q.pitch, s.M, 64, kWgPB);
   CUtensorMap mQ1 = make_rows_map(s.Q.lo, s.Q.pitch, s.M, 64, kWgPB);
   CUtensorMap mD = make_rows_map_f32(part, nqmax, (long long)ng * gx * s.np, 32, 128);
-  Prof pf(c, F_WGRAD_TC, 2, 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
+  Prof pf(c, F_WGRAD_TC, 1, 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
   dim3 grid(gx, ng, 1);
   if (NT == 3) {
     INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -293,11 +305,25 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) {
     k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   }
   INB_CUDA(cudaGetLastError());
-  const long long outs = (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
-  k_wgrad_reduce<<<(unsigned)std::min<long long>(cdiv(outs, 64), 148 * 8), 256, 0, c.st>>>(
-      part, (int)gx, s.np, nqmax, a.qtot, s.C, s.T, s.dw, a.dbpart, s.db);
-  INB_CUDA(cudaGetLastError());
+  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, s.dw, a.dbpart, s.db};
+  return (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
+}
+
+// n (<= 3) weight gradients: their split-K kernels back to back, then ONE reduction launch (grid row = gradient)
+void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n) {
+  INB_CHECK(n >= 1 && n <= 3, "wgrad: 1 to 3 gradients per call");
+  size_t mk = c.ar->mark();
+  WgradReduceArgs ra{};
+  long long outs = 0;
+  for (int i = 0; i < n; ++i) outs = std::max(outs, wgrad2_launch(c, specs[i], ra.d[i]));
+  if (!c.dry()) {
+    Prof pf(c, F_WGRAD_TC, 1, 0, 0);
+    dim3 grid((unsigned)std::min<long long>(cdiv(outs, 64), 148 * 4), (unsigned)n, 1);
+    k_wgrad_reduce<<<grid, 256, 0, c.st>>>(ra);
+    INB_CUDA(cudaGetLastError());
+  }
   c.ar->release(mk);
 }
+void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s) { op_wgrad2_tc_multi(c, &s, 1); }
 
 }  // namespace inb

@@ -294,9 +294,11 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
     cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
     op_rb_chain(c, cs);
-    op_wgrad2_tc(c, Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr});   // :152
-    op_wgrad2_tc(c, Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2});           // :156-157
-    op_wgrad2_tc(c, Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1});      // :163-164
+    const Wgrad2TcSpec wg[3] = {
+        Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr},   // :152
+        Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2},           // :156-157
+        Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1}};     // :163-164
+    op_wgrad2_tc_multi(c, wg, 3);
     c.ar->release(m);
     return;
   }
