@@ -159,6 +159,66 @@ int inb_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C, int n
 int inb_squeeze(int ndims, int nx, int ny, int nz, int B, int C, const float* X, float* Y, void* stream);
 int inb_unsqueeze(int ndims, int nx, int ny, int nz, int B, int C, const float* Y, float* X, void* stream);
 
+/* ------------------------------------------------------------------ HINT family
+ * Haar squeezes, 2-D: type 0 = wavelet_squeeze / wavelet_unsqueeze with WT.db1 (dimensionality_operations.jl:199-258,
+ * channel 4c+q, q = approximation, x detail, y detail, diagonal), type 1 = Haar_squeeze / invHaar_unsqueeze
+ * (:318-371, channel q*C+c, q = a, v, h, d).  (nx, ny, C) describe X for the squeeze and Y for the unsqueeze. */
+#define INB_SQUEEZE_WAVELET 0
+#define INB_SQUEEZE_HAAR 1
+int inb_haar_squeeze(int nx, int ny, int B, int C, int type, const float* X, float* Y, void* stream);
+int inb_haar_unsqueeze(int nx, int ny, int B, int C, int type, const float* Y, float* X, void* stream);
+
+/* CouplingLayerHINT (invertible_layer_hint.jl:52-297) over CouplingLayerBasic (invertible_layer_basic.jl:62-149).
+ * hparams = {CL[1].RB.(W1,W2,W3,b1,b2), ..., CL[n].RB.(...), [C.v1, C.v2, C.v3]} - the layer's get_params order,
+ * n = inb_hint_depth(C) (get_depth, :63-71), the Conv1x1 entries present when permute != none; CL[j] acts on
+ * C/2^j channels.  permute: 0 none, 1 full, 2 lower ("both" stays on the reference).
+ * shared_grads: a CL[j], j > 1, is applied 2^(j-1) times per pass; 0 = its gradient is the sum over the visits (the true
+ * gradient; the reference's set_grad=false path, :222), 1 = only the last visit survives (what the reference's
+ * set_grad=true path leaves in .grad, layer_residual_block.jl:168-172). */
+#define INB_PERMUTE_NONE 0
+#define INB_PERMUTE_FULL 1
+#define INB_PERMUTE_LOWER 2
+int inb_hint_depth(int C);
+int inb_hint_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                              float high, int permute, int precision, const float* X, float* const* hparams,
+                              float* Y, float* logdet /* nullable */, void* stream);
+int inb_hint_coupling_inverse(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                              float high, int permute, int precision, const float* Y, float* const* hparams,
+                              float* X, void* stream);
+int inb_hint_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                               float high, int permute, int logdet, int shared_grads, int precision,
+                               const float* dY, const float* Y, float* const* hparams, float* const* hgrads,
+                               float* dX, float* X, void* stream);
+
+/* NetworkMultiScaleHINT (invertible_network_hint_multiscale.jl:55-174), 2-D: per scale a Haar squeeze, then K x
+ * (ActNorm, CouplingLayerHINT with permute = "full", logdet = true).  params / grads in get_params order:
+ * AN[i,j].(s,b) for i = 1..L, j = 1..K, then CL[i,j].(CL[1..n_i].RB.(W1,W2,W3,b1,b2), C.(v1,v2,v3)). */
+typedef struct inb_hint_plan inb_hint_plan;
+typedef struct inb_hint_desc {
+  int nx, ny;         /* input spatial size */
+  int n_in;           /* input channels */
+  int n_hidden;
+  int L, K;
+  int batch;          /* batch size the workspace is sized for */
+  int split_scales;   /* :74-82: split half the channels off after every scale but the last */
+  int k1, k2, p1, p2; /* ResidualBlock kernels ("same" padding); the reference's default is 3,3,1,1 */
+  float sig_low, sig_high;
+  int squeeze_type;   /* INB_SQUEEZE_*; the reference uses wavelet_squeeze (:102) */
+  int shared_grads;   /* see inb_hint_coupling_backward */
+  int precision;      /* INB_PREC_* */
+} inb_hint_desc;
+int inb_hint_plan_create(const inb_hint_desc* desc, inb_hint_plan** plan);
+int inb_hint_plan_destroy(inb_hint_plan* plan);
+int inb_hint_num_params(const inb_hint_plan* plan);
+int inb_hint_param_numel(const inb_hint_plan* plan, int index, long long* numel);
+long long inb_hint_workspace_bytes(const inb_hint_plan* plan);
+/* Z: flat, X's element count ([vec(Z_1);..;vec(X_L)] when split_scales, else the (B, n_in*4^L, ny/2^L, nx/2^L) tensor) */
+int inb_hint_forward(inb_hint_plan* plan, int batch, const float* X, float* const* params, float* Z,
+                     float* logdet, int init_actnorm, void* stream);
+int inb_hint_inverse(inb_hint_plan* plan, int batch, const float* Z, float* const* params, float* X, void* stream);
+int inb_hint_backward(inb_hint_plan* plan, int batch, const float* dZ, const float* Z, float* const* params,
+                      float* const* grads, float* dX, float* X, void* stream);
+
 /* Gaussian negative log-likelihood value and gradient, objective_functions.jl:54,65:
  * loss = sum(Z^2)/(2B) (device float, nullable), dZ = Z/B. */
 int inb_nll_grad(long long n, int B, const float* Z, float* dZ, float* loss, void* stream);

@@ -1004,4 +1004,363 @@ int inb_adam_update(long long n, float* params, const float* grads, float* m, fl
   });
 }
 
+// ====================================================================== HINT family
+int inb_haar_squeeze(int nx, int ny, int B, int C, int type, const float* X, float* Y, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && B > 0 && C > 0, "bad argument");
+    Geo g = make_geo(2, nx, ny, 1);
+    Arena a;
+    Ctx c{(cudaStream_t)stream, &a, 0};
+    op_haar_squeeze(c, g, B, C, type, view(const_cast<float*>(X), C * g.px), view(Y, C * g.px));
+  });
+}
+int inb_haar_unsqueeze(int nx, int ny, int B, int C, int type, const float* Y, float* X, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && B > 0 && C > 0, "bad argument");
+    INB_CHECK(C % 4 == 0, "number of channels must be divisible by 4");
+    Geo g = make_geo(2, nx * 2, ny * 2, 1);
+    Arena a;
+    Ctx c{(cudaStream_t)stream, &a, 0};
+    op_haar_unsqueeze(c, g, B, C / 4, type, view(const_cast<float*>(Y), (C / 4) * g.px), view(X, (C / 4) * g.px));
+  });
+}
+
+static HintShape hint_shape(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                            float high, int permute, int logdet, int shared) {
+  INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+  INB_CHECK(B > 0 && nh > 0, "bad shape");
+  INB_CHECK((k1 == 1 || k1 == 3) && (k2 == 1 || k2 == 3), "supported kernel sizes are 1 and 3");
+  INB_CHECK(high > low, "sigmoid high must exceed low");
+  HintShape h{};
+  h.g = make_geo(ndims, nx, ny, nz);
+  h.B = B; h.C = C; h.nh = nh; h.k1 = k1; h.k2 = k2; h.low = low; h.high = high;
+  h.logdet = logdet; h.permute = permute; h.shared_last = shared;
+  hint_check(h);
+  return h;
+}
+// table in the layer's get_params order -> HintParams / HintGrads
+static HintParams hint_params(const HintShape& h, float* const* t) {
+  HintParams p;
+  const int n = h.depth();
+  p.cl.resize(n);
+  if (!t) return p;
+  for (int j = 0; j < n; ++j) p.cl[j] = RBParams{t[5 * j], t[5 * j + 1], t[5 * j + 2], t[5 * j + 3], t[5 * j + 4]};
+  if (h.permute != HINT_PERMUTE_NONE) { p.v1 = t[5 * n]; p.v2 = t[5 * n + 1]; p.v3 = t[5 * n + 2]; }
+  return p;
+}
+static HintGrads hint_grads(const HintShape& h, float* const* t) {
+  HintGrads g;
+  const int n = h.depth();
+  g.cl.resize(n);
+  if (!t) return g;
+  for (int j = 0; j < n; ++j) g.cl[j] = RBGrads{t[5 * j], t[5 * j + 1], t[5 * j + 2], t[5 * j + 3], t[5 * j + 4]};
+  if (h.permute != HINT_PERMUTE_NONE) { g.v1 = t[5 * n]; g.v2 = t[5 * n + 1]; g.v3 = t[5 * n + 2]; }
+  return g;
+}
+
+int inb_hint_depth(int C) {
+  HintShape h{};
+  h.C = C;
+  return h.depth();
+}
+int inb_hint_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                              float high, int permute, int precision, const float* X, float* const* hparams,
+                              float* Y, float* logdet, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && hparams, "null argument");
+    HintShape h = hint_shape(ndims, nx, ny, nz, B, C, nh, k1, k2, low, high, permute, logdet != nullptr, 0);
+    HintParams p = hint_params(h, hparams);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      double* ld = logdet ? c.ar->f64(1) : nullptr;
+      if (ld) op_zero(c, ld, sizeof(double));
+      hint_forward(c, h, view(const_cast<float*>(X), C * h.g.px), view(Y, C * h.g.px), p, ld);
+      if (ld) op_ld_finish(c, ld, logdet);
+    });
+  });
+}
+int inb_hint_coupling_inverse(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                              float high, int permute, int precision, const float* Y, float* const* hparams,
+                              float* X, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X && Y && hparams, "null argument");
+    HintShape h = hint_shape(ndims, nx, ny, nz, B, C, nh, k1, k2, low, high, permute, 0, 0);
+    HintParams p = hint_params(h, hparams);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      View x = view(X, C * h.g.px);
+      op_copy(c, h.g.px, B, C, view(const_cast<float*>(Y), C * h.g.px), x);
+      hint_inverse(c, h, x, x, p);
+    });
+  });
+}
+int inb_hint_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
+                               float high, int permute, int logdet, int shared_grads, int precision,
+                               const float* dY, const float* Y, float* const* hparams, float* const* hgrads,
+                               float* dX, float* X, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY && Y && dX && X && hparams && hgrads, "null argument");
+    HintShape h = hint_shape(ndims, nx, ny, nz, B, C, nh, k1, k2, low, high, permute, logdet, shared_grads);
+    HintParams p = hint_params(h, hparams);
+    HintGrads g = hint_grads(h, hgrads);
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      const long long bs = C * h.g.px;
+      View x = view(X, bs), dx = view(dX, bs);
+      op_copy(c, h.g.px, B, C, view(const_cast<float*>(Y), bs), x);
+      op_copy(c, h.g.px, B, C, view(const_cast<float*>(dY), bs), dx);
+      hint_backward(c, h, dx, x, dx, x, p, g);
+    });
+  });
+}
+
+// ---------------------------------------------------------------- NetworkMultiScaleHINT
+struct HintScale {
+  Geo g;
+  int C;     // channels of the flow steps
+  int kc;    // channels that continue to the next scale (== C when nothing is split off)
+  int depth;
+  int pbase; // index of CL[i,1]'s first parameter
+};
+struct inb_hint_plan {
+  inb_hint_desc d;
+  Geo g0;
+  std::vector<HintScale> sc;
+  int nparams = 0;
+  Arena ar;
+  size_t need = 0, persist = 0;
+  double* ld = nullptr;
+};
+
+static HintShape hplan_shape(const inb_hint_plan* p, int i, int B) {
+  const HintScale& s = p->sc[i];
+  HintShape h{};
+  h.g = s.g; h.B = B; h.C = s.C; h.nh = p->d.n_hidden; h.k1 = p->d.k1; h.k2 = p->d.k2;
+  h.low = p->d.sig_low; h.high = p->d.sig_high; h.logdet = 1; h.permute = HINT_PERMUTE_FULL;
+  h.shared_last = p->d.shared_grads;
+  return h;
+}
+static int hplan_cl_base(const inb_hint_plan* p, int i, int j) { return p->sc[i].pbase + j * (5 * p->sc[i].depth + 3); }
+static HintParams hplan_params(const inb_hint_plan* p, int i, int j, float* const* t) {
+  HintShape h = hplan_shape(p, i, 1);
+  HintParams hp = hint_params(h, t ? t + hplan_cl_base(p, i, j) : nullptr);
+  if (t) { hp.s = t[2 * (i * p->d.K + j)]; hp.b = t[2 * (i * p->d.K + j) + 1]; }
+  return hp;
+}
+static HintGrads hplan_grads(const inb_hint_plan* p, int i, int j, float* const* t) {
+  HintShape h = hplan_shape(p, i, 1);
+  HintGrads hg = hint_grads(h, t ? t + hplan_cl_base(p, i, j) : nullptr);
+  if (t) { hg.s = t[2 * (i * p->d.K + j)]; hg.b = t[2 * (i * p->d.K + j) + 1]; }
+  return hg;
+}
+static long long hplan_zoff(const inb_hint_plan* p, int B, int upto) {
+  long long off = 0;
+  for (int i = 0; i < upto && i < (int)p->sc.size(); ++i) off += (long long)B * (p->sc[i].C - p->sc[i].kc) * p->sc[i].g.px;
+  return off;
+}
+
+static void hint_drive_forward(inb_hint_plan* p, Ctx& c, int B, const float* X, float* const* prm, float* Z,
+                               float* logdet, int init) {
+  const inb_hint_desc& d = p->d;
+  const long long tot = (long long)d.n_in * p->g0.px;
+  size_t m = c.ar->mark();
+  float* buf[2] = {c.ar->f32((size_t)B * tot), c.ar->f32((size_t)B * tot)};
+  op_zero(c, p->ld, sizeof(double));
+  View cur = view(const_cast<float*>(X), tot);
+  int which = 0, chan = d.n_in;
+  Geo g = p->g0;
+  for (int i = 0; i < d.L; ++i) {
+    const HintScale& s = p->sc[i];
+    const long long bs = (long long)s.C * s.g.px;
+    {
+      View out = view(buf[which], bs);
+      op_haar_squeeze(c, g, B, chan, d.squeeze_type, cur, out);  // hint_multiscale.jl:102
+      cur = out;
+      which ^= 1;
+    }
+    const HintShape h = hplan_shape(p, i, B);
+    for (int j = 0; j < d.K; ++j) {
+      HintParams hp = hplan_params(p, i, j, prm);
+      if (init) op_actnorm_init(c, s.g.px, B, s.C, cur, const_cast<float*>(hp.s), const_cast<float*>(hp.b));
+      View out = view(buf[which], bs);
+      hint_forward(c, h, cur, out, hp, p->ld);  // :104-106
+      cur = out;
+      which ^= 1;
+    }
+    if (s.kc != s.C)  // :108-112: X = first part, Z = second part
+      op_copy(c, s.g.px, B, s.C - s.kc, sub(cur, s.kc, s.g.px), view(Z + hplan_zoff(p, B, i), (long long)(s.C - s.kc) * s.g.px));
+    chan = s.kc;
+    g = s.g;
+  }
+  {
+    const HintScale& s = p->sc[d.L - 1];
+    op_copy(c, s.g.px, B, chan, cur, view(Z + hplan_zoff(p, B, d.L), (long long)chan * s.g.px));  // :114
+  }
+  if (logdet) op_ld_finish(c, p->ld, logdet);
+  c.ar->release(m);
+}
+
+static void hint_drive_reverse(inb_hint_plan* p, Ctx& c, int B, bool grads, const float* dZ, const float* Z,
+                               float* const* prm, float* const* gr, float* dX, float* X) {
+  const inb_hint_desc& d = p->d;
+  const long long tot = (long long)d.n_in * p->g0.px;
+  size_t m = c.ar->mark();
+  float* yb[2] = {c.ar->f32((size_t)B * tot), c.ar->f32((size_t)B * tot)};
+  float* db[2] = {nullptr, nullptr};
+  if (grads) { db[0] = c.ar->f32((size_t)B * tot); db[1] = c.ar->f32((size_t)B * tot); }
+  int which = 0;
+  {
+    const HintScale& sl = p->sc[d.L - 1];
+    const long long off = hplan_zoff(p, B, d.L), bs = (long long)sl.C * sl.g.px;
+    op_copy(c, sl.g.px, B, sl.C, view(const_cast<float*>(Z) + off, bs), view(yb[which], bs));
+    if (grads) op_copy(c, sl.g.px, B, sl.C, view(const_cast<float*>(dZ) + off, bs), view(db[which], bs));
+  }
+  for (int i = d.L - 1; i >= 0; --i) {
+    const HintScale& s = p->sc[i];
+    const long long bs = (long long)s.C * s.g.px;
+    View y = view(yb[which], bs), dy = view(grads ? db[which] : nullptr, bs);
+    if (s.kc != s.C) {  // :144-147 tensor_cat with the saved latent
+      const long long off = hplan_zoff(p, B, i);
+      const int zc = s.C - s.kc;
+      op_copy(c, s.g.px, B, zc, view(const_cast<float*>(Z) + off, (long long)zc * s.g.px), sub(y, s.kc, s.g.px));
+      if (grads) op_copy(c, s.g.px, B, zc, view(const_cast<float*>(dZ) + off, (long long)zc * s.g.px), sub(dy, s.kc, s.g.px));
+    }
+    const HintShape h = hplan_shape(p, i, B);
+    for (int j = d.K - 1; j >= 0; --j) {
+      HintParams hp = hplan_params(p, i, j, prm);
+      if (grads) hint_backward(c, h, dy, y, dy, y, hp, hplan_grads(p, i, j, gr));  // :150-152
+      else hint_inverse(c, h, y, y, hp);                                          // :127-130
+    }
+    // wavelet_unsqueeze (:131, :163-164) into the first channels of the coarser scale's buffer / the caller's output
+    const Geo gout = (i == 0) ? p->g0 : p->sc[i - 1].g;
+    const long long obs = (i == 0) ? tot : (long long)p->sc[i - 1].C * p->sc[i - 1].g.px;
+    op_haar_unsqueeze(c, gout, B, s.C / 4, d.squeeze_type, y, view(i == 0 ? X : yb[which ^ 1], obs));
+    if (grads) op_haar_unsqueeze(c, gout, B, s.C / 4, d.squeeze_type, dy, view(i == 0 ? dX : db[which ^ 1], obs));
+    which ^= 1;
+  }
+  c.ar->release(m);
+}
+
+static Ctx hint_call_ctx(inb_hint_plan* p, void* stream) {
+  if (!p->ar.base) {
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, p->need);
+    if (e != cudaSuccess) fail(INB_ERR_NOMEM, "workspace of %zu bytes: %s", p->need, cudaGetErrorString(e));
+    p->ar.base = (char*)base;
+    p->ar.cap = p->need;
+    p->ar.dry = false;
+    p->ar.off = 0;
+    p->ld = (double*)p->ar.alloc_bytes(256);
+    p->persist = p->ar.off;
+  }
+  p->ar.off = p->persist;
+  return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
+}
+static void hint_check_call(inb_hint_plan* p, int batch) {
+  INB_CHECK(p != nullptr, "null plan");
+  INB_CHECK(batch >= 1 && batch <= p->d.batch, "batch %d outside the plan's range [1, %d]", batch, p->d.batch);
+}
+
+int inb_hint_plan_create(const inb_hint_desc* d, inb_hint_plan** out) {
+  return guarded([&] {
+    INB_CHECK(out != nullptr, "null output");
+    *out = nullptr;
+    INB_CHECK(d != nullptr, "null descriptor");
+    INB_CHECK(d->nx > 0 && d->ny > 0 && d->n_in >= 1 && d->n_hidden >= 1 && d->L >= 1 && d->K >= 1 && d->batch >= 1,
+              "nx, ny, n_in, n_hidden, L, K, batch must be >= 1");
+    INB_CHECK((d->k1 == 1 || d->k1 == 3) && (d->k2 == 1 || d->k2 == 3),
+              "supported ResidualBlock kernel sizes are 1 and 3 (got k1=%d k2=%d)", d->k1, d->k2);
+    INB_CHECK(d->p1 == (d->k1 - 1) / 2 && d->p2 == (d->k2 - 1) / 2, "only 'same' padding is supported");
+    INB_CHECK(d->precision >= 0 && d->precision <= 2, "unknown precision mode %d", d->precision);
+    INB_CHECK(d->sig_high > d->sig_low, "sigmoid high must exceed low");
+    INB_CHECK(d->squeeze_type == 0 || d->squeeze_type == 1, "squeeze_type must be 0 (wavelet) or 1 (Haar)");
+    std::unique_ptr<inb_hint_plan> p(new inb_hint_plan());
+    p->d = *d;
+    p->g0 = make_geo(2, d->nx, d->ny, 1);
+    Geo g = p->g0;
+    int chan = d->n_in, idx = 2 * d->L * d->K;
+    for (int i = 0; i < d->L; ++i) {
+      INB_CHECK(!(g.W % 2) && !(g.H % 2), "Input dimensions must be multiple of 2");
+      HintScale s{};
+      s.g = half_geo(g);
+      s.C = 4 * chan;  // ctor :87
+      s.kc = (d->split_scales && i < d->L - 1) ? s.C / 2 : s.C;
+      p->sc.push_back(s);
+      HintShape h = hplan_shape(p.get(), i, d->batch);
+      hint_check(h);
+      p->sc[i].depth = h.depth();
+      p->sc[i].pbase = idx;
+      idx += d->K * (5 * h.depth() + 3);
+      chan = s.kc;
+      g = s.g;
+    }
+    p->nparams = idx;
+    Arena dry;
+    dry.dry = true;
+    dry.alloc_bytes(256);
+    Ctx dc{nullptr, &dry, p->d.precision};
+    hint_drive_forward(p.get(), dc, d->batch, nullptr, nullptr, nullptr, nullptr, 1);
+    hint_drive_reverse(p.get(), dc, d->batch, true, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    p->need = dry.peak + 1024;
+    *out = p.release();
+  });
+}
+int inb_hint_plan_destroy(inb_hint_plan* p) {
+  return guarded([&] {
+    if (!p) return;
+    if (p->ar.base) cudaFree(p->ar.base);
+    delete p;
+  });
+}
+int inb_hint_num_params(const inb_hint_plan* p) { return p ? p->nparams : -1; }
+long long inb_hint_workspace_bytes(const inb_hint_plan* p) { return p ? (long long)p->need : -1; }
+int inb_hint_param_numel(const inb_hint_plan* p, int index, long long* numel) {
+  return guarded([&] {
+    INB_CHECK(p && numel && index >= 0 && index < p->nparams, "bad argument");
+    const inb_hint_desc& d = p->d;
+    if (index < 2 * d.L * d.K) {
+      *numel = p->sc[index / (2 * d.K)].C;
+      return;
+    }
+    for (int i = d.L - 1; i >= 0; --i) {
+      if (index < p->sc[i].pbase) continue;
+      const HintScale& s = p->sc[i];
+      const int per = 5 * s.depth + 3, w = (index - s.pbase) % per;
+      if (w >= 5 * s.depth) { *numel = s.C; return; }
+      const int j = w / 5 + 1, c = s.C >> j;  // CL[j] = CouplingLayerBasic(C / 2^j), hint.jl:86
+      const long long t1 = (long long)d.k1 * d.k1, t2 = (long long)d.k2 * d.k2, nh = d.n_hidden;
+      switch (w % 5) {
+        case 0: *numel = nh * c * t1; break;
+        case 1: *numel = nh * nh * t2; break;
+        case 2: *numel = nh * 2 * c * t1; break;
+        default: *numel = nh;
+      }
+      return;
+    }
+  });
+}
+int inb_hint_forward(inb_hint_plan* p, int batch, const float* X, float* const* params, float* Z, float* logdet,
+                     int init_actnorm, void* stream) {
+  return guarded([&] {
+    hint_check_call(p, batch);
+    INB_CHECK(X && params && Z, "null tensor argument");
+    Ctx c = hint_call_ctx(p, stream);
+    hint_drive_forward(p, c, batch, X, params, Z, logdet, init_actnorm);
+  });
+}
+int inb_hint_inverse(inb_hint_plan* p, int batch, const float* Z, float* const* params, float* X, void* stream) {
+  return guarded([&] {
+    hint_check_call(p, batch);
+    INB_CHECK(X && params && Z, "null tensor argument");
+    Ctx c = hint_call_ctx(p, stream);
+    hint_drive_reverse(p, c, batch, false, nullptr, Z, params, nullptr, nullptr, X);
+  });
+}
+int inb_hint_backward(inb_hint_plan* p, int batch, const float* dZ, const float* Z, float* const* params,
+                      float* const* grads, float* dX, float* X, void* stream) {
+  return guarded([&] {
+    hint_check_call(p, batch);
+    INB_CHECK(dZ && Z && params && grads && dX && X, "null tensor argument");
+    Ctx c = hint_call_ctx(p, stream);
+    hint_drive_reverse(p, c, batch, true, dZ, Z, params, grads, dX, X);
+  });
+}
+
 }  // extern "C"

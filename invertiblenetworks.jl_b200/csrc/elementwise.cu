@@ -123,6 +123,90 @@ void op_unsqueeze(Ctx& c, const Geo& g, int B, int C, View in, View out) {
   INB_CUDA(cudaGetLastError());
 }
 
+// One-level orthonormal Haar transform of every (sample, channel) image followed by the patch squeeze, 2-D.
+// wavelet_squeeze (dimensionality_operations.jl:199-216, WT.db1) and Haar_squeeze (:318-331) compute the same four
+// butterflies of a 2x2 block and differ in the output channel order only:
+//   a  = (p00 + p10 + p01 + p11) / 2       p[ix][iy] = in[2x'+ix, 2y'+iy]
+//   dx = (p00 - p10 + p01 - p11) / 2       detail along x (HaarLift(., 1): first - second, :272-281)
+//   dy = (p00 + p10 - p01 - p11) / 2       detail along y
+//   dd = (p00 - p10 - p01 + p11) / 2
+// TYPE 0 (wavelet): channel 4c + q, q = (a, dx, dy, dd) - the quadrants of dwt() in patch order (:30-36)
+// TYPE 1 (Haar lifting): channel q*C + c, q = (a, v = dy, h = dx, d = dd) - cat(a, v, h, d) of :330
+// One thread owns one half-resolution pixel of one (b, c): two 8-byte accesses on the full-resolution side, four
+// 4-byte accesses (coalesced over x') on the squeezed side.
+template <bool FWD>
+__global__ void k_haar(const float* __restrict__ src, long long sbs, float* __restrict__ dst, long long dbs, int C,
+                       int W, int H, int B, int type) {
+  const int Wh = W >> 1, Hh = H >> 1;
+  const long long pxf = (long long)W * H, pxh = pxf >> 2;
+  const long long total = (long long)B * C * Hh * Wh;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int xh = (int)(t % Wh); t /= Wh;
+    const int yh = (int)(t % Hh); t /= Hh;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    const long long full = (long long)b * (FWD ? sbs : dbs) + (long long)c * pxf + (long long)(2 * yh) * W + 2 * xh;
+    const long long half = (long long)b * (FWD ? dbs : sbs) + (long long)yh * Wh + xh;
+    long long ch[4];  // squeezed-side channel of (a, dx, dy, dd)
+    if (type == 0) {
+      ch[0] = 4LL * c; ch[1] = 4LL * c + 1; ch[2] = 4LL * c + 2; ch[3] = 4LL * c + 3;
+    } else {
+      ch[0] = c; ch[1] = 2LL * C + c; ch[2] = (long long)C + c; ch[3] = 3LL * C + c;
+    }
+    if (FWD) {
+      const float2 r0 = *reinterpret_cast<const float2*>(src + full);      // p00 p10
+      const float2 r1 = *reinterpret_cast<const float2*>(src + full + W);  // p01 p11
+      const float s0 = r0.x + r0.y, d0 = r0.x - r0.y, s1 = r1.x + r1.y, d1 = r1.x - r1.y;
+      dst[half + ch[0] * pxh] = 0.5f * (s0 + s1);
+      dst[half + ch[1] * pxh] = 0.5f * (d0 + d1);
+      dst[half + ch[2] * pxh] = 0.5f * (s0 - s1);
+      dst[half + ch[3] * pxh] = 0.5f * (d0 - d1);
+    } else {
+      const float a = src[half + ch[0] * pxh], dx = src[half + ch[1] * pxh];
+      const float dy = src[half + ch[2] * pxh], dd = src[half + ch[3] * pxh];
+      const float s0 = a + dy, s1 = a - dy, d0 = dx + dd, d1 = dx - dd;
+      *reinterpret_cast<float2*>(dst + full) = make_float2(0.5f * (s0 + d0), 0.5f * (s0 - d0));
+      *reinterpret_cast<float2*>(dst + full + W) = make_float2(0.5f * (s1 + d1), 0.5f * (s1 - d1));
+    }
+  }
+}
+static void haar_check(const Geo& g, View full) {
+  INB_CHECK(g.nd == 2, "the Haar / wavelet squeeze is implemented for 2-D tensors only");
+  INB_CHECK(!(g.W % 2) && !(g.H % 2), "Input dimensions must be multiple of 2");
+  INB_CHECK(full.bs % 2 == 0 && ((uintptr_t)full.p & 7) == 0, "Haar squeeze: full-resolution tensor must be 8-byte aligned");
+}
+// g = full-resolution geometry, C = full-resolution channels
+void op_haar_squeeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out) {
+  INB_CHECK(type == 0 || type == 1, "squeeze type must be 0 (wavelet db1) or 1 (Haar lifting)");
+  if (c.dry()) { INB_CHECK(g.nd == 2 && !(g.W % 2) && !(g.H % 2), "Input dimensions must be multiple of 2 (2-D only)"); return; }
+  haar_check(g, in);
+  Prof pf(c, F_SQUEEZE, 1, 0, 8.0 * B * C * g.px);
+  k_haar<true><<<grid_for((long long)B * C * (g.px / 4), 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, B, type);
+  INB_CUDA(cudaGetLastError());
+}
+void op_haar_unsqueeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out) {
+  INB_CHECK(type == 0 || type == 1, "squeeze type must be 0 (wavelet db1) or 1 (Haar lifting)");
+  if (c.dry()) return;
+  haar_check(g, out);
+  Prof pf(c, F_SQUEEZE, 1, 0, 8.0 * B * C * g.px);
+  k_haar<false><<<grid_for((long long)B * C * (g.px / 4), 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, B, type);
+  INB_CUDA(cudaGetLastError());
+}
+
+// dst += src (gradients of a coupling layer that the HINT recursion visits more than once)
+__global__ void k_accum(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+void op_accum(Ctx& c, long long n, const float* src, float* dst) {
+  if (c.dry() || n == 0) return;
+  Prof pf(c, F_MISC, 1, 0, 12.0 * n);
+  k_accum<<<grid_for(n, 256), 256, 0, c.st>>>(src, dst, n);
+  INB_CUDA(cudaGetLastError());
+}
+
 template <int V>
 __global__ void k_copy(const float* __restrict__ src, long long sbs, float* __restrict__ dst,
                        long long dbs, long long per_sample /* C*px */, int B) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "ops.cuh"
 #include "conv_tc.cuh"
+#include <vector>
 
 namespace inb {
 
@@ -80,5 +81,37 @@ void flow_inverse(Ctx& c, const FlowShape& f, View y, View x, View cond, const F
 // backward of both; (dy, y) are clobbered and (dx, x) may alias them
 void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x, View cond, View dcond,
                    const FlowParams& p, const FlowGrads& g);
+
+// ---------------------------------------------------------------- HINT family (hint.cu)
+// CouplingLayerHINT (invertible_layer_hint.jl:52-300) over CouplingLayerBasic (invertible_layer_basic.jl:62-166),
+// all on channel-range views of ONE tensor (no tensor_split / tensor_cat copies).
+enum { HINT_PERMUTE_NONE = 0, HINT_PERMUTE_FULL = 1, HINT_PERMUTE_LOWER = 2 };
+struct HintShape {
+  Geo g;
+  int B, C, nh, k1, k2;
+  float low, high;
+  int logdet;
+  int permute;       // HINT_PERMUTE_*
+  int shared_last;   // 1: gradients of a coupling layer visited several times keep the LAST visit only (the
+                     // reference's set_grad=true, layer_residual_block.jl:168-172); 0: they are summed (hint.jl:222)
+  int depth() const;  // get_depth, hint.jl:63-71
+};
+struct HintParams {
+  std::vector<RBParams> cl;  // CL[1..depth].RB
+  const float *v1 = nullptr, *v2 = nullptr, *v3 = nullptr;  // C (permute full / lower)
+  const float *s = nullptr, *b = nullptr;  // an ActNorm in front (NetworkMultiScaleHINT), fused with `full`
+};
+struct HintGrads {
+  std::vector<RBGrads> cl;
+  float *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *s = nullptr, *b = nullptr;
+};
+void hint_check(const HintShape& h);
+// [ActNorm ->] CouplingLayerHINT.forward: x -> y (y != x); ld accumulates both logdets
+void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& p, double* ld);
+// CouplingLayerHINT.inverse [-> ActNorm.inverse]: y (clobbered) -> x (may alias y)
+void hint_inverse(Ctx& c, const HintShape& h, View y, View x, const HintParams& p);
+// backward of both: (dy, y) clobbered, (dx, x) may alias them
+void hint_backward(Ctx& c, const HintShape& h, View dy, View y, View dx, View x, const HintParams& p,
+                   const HintGrads& g);
 
 }  // namespace inb

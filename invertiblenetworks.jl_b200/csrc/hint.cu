@@ -1,0 +1,192 @@
+// hint.cu - the HINT family on the kernels of the Glow path: CouplingLayerBasic (invertible_layer_basic.jl:90-149)
+// and the recursive CouplingLayerHINT (invertible_layer_hint.jl:105-297).
+//
+// The reference recursion splits and concatenates tensors at every level; here every level works on channel-range
+// views of ONE tensor in place.  That needs a different execution order inside a level than the reference's
+// (whose statements are independent where reordered):
+//   forward   Xb <- HINT(Xb) ; Xb <- CL[s](Xa, Xb) ; Xa <- HINT(Xa)     (hint.jl:131-133: the coupling reads the
+//                                                                        UNTRANSFORMED Xa, so Xa goes last)
+//   inverse   Ya <- HINT^-1(Ya) ; Yb <- CL[s]^-1(Xa, Yb) ; Yb <- HINT^-1(Yb)                       (:172-178)
+//   backward  (dYa,Ya) <- HINT.bwd ; CL[s].bwd adds into dXa and maps (dYb,Yb) ; (dYb,Yb) <- HINT.bwd  (:230-232,248)
+// The affine coupling itself is the Glow coupling with the roles of the halves exchanged (the FIRST half conditions,
+// the SECOND is transformed), so the same three kernels serve (op_coupling_fwd / inv / bwd).
+#include "glow.cuh"
+
+namespace inb {
+
+int HintShape::depth() const {
+  int count = 0;
+  double nc = C;
+  while (nc > 4) { nc /= 2; ++count; }
+  return count + 1;
+}
+
+void hint_check(const HintShape& h) {
+  INB_CHECK(h.C >= 2, "CouplingLayerHINT needs at least 2 channels (got %d)", h.C);
+  INB_CHECK(h.permute >= 0 && h.permute <= 2, "permute must be none (0), full (1) or lower (2); 'both' stays on the reference");
+  // Int(n_in/2^j) must be exact (hint.jl:86) and every level must split into equal halves
+  const int n = h.depth();
+  INB_CHECK(h.C % (1 << n) == 0 || (h.C <= 4 && h.C % 2 == 0),
+            "CouplingLayerHINT: %d channels cannot be halved %d times (InexactError in the reference)", h.C, n);
+}
+
+static RBShape basic_rb(const HintShape& h, int Ca) {
+  return RBShape{h.g, h.B, Ca, 0, h.nh, 2 * Ca, h.k1, h.k2};
+}
+
+// CL.forward(X1 = xa, X2 = xb): xb <- S .* xb + T                        basic.jl:96-98
+static void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld) {
+  const RBShape rs = basic_rb(h, Ca);
+  size_t m = c.ar->mark();
+  RBHidden hid;
+  hid.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  hid.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  hid.G = nullptr;
+  float* Y3 = c.ar->f32((size_t)h.B * rs.Cout * h.g.px);
+  rb_forward(c, rs, xa, view(nullptr, 0), p, hid, Y3);
+  op_coupling_fwd(c, h.g.px, h.B, Ca, xb, xb, Y3, h.low, h.high, h.logdet ? ld : nullptr);
+  c.ar->release(m);
+}
+// CL.inverse(Y1 = xa, Y2 = yb): yb <- (yb - T) ./ (S + eps)               basic.jl:112-114
+static void basic_inverse(Ctx& c, const HintShape& h, int Ca, View xa, View yb, const RBParams& p) {
+  const RBShape rs = basic_rb(h, Ca);
+  size_t m = c.ar->mark();
+  RBHidden hid;
+  hid.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  hid.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  hid.G = nullptr;
+  float* Y3 = c.ar->f32((size_t)h.B * rs.Cout * h.g.px);
+  rb_forward(c, rs, xa, view(nullptr, 0), p, hid, Y3);
+  op_coupling_inv(c, h.g.px, h.B, Ca, yb, yb, Y3, h.low, h.high);
+  c.ar->release(m);
+}
+// CL.backward(dY1 = 0, dY2 = dyb, Y1 = xa, Y2 = yb) with its dX1 ADDED to dxa (hint.jl:231,248 / :253,264):
+// (dyb, yb) <- (dX2, X2) in place                                          basic.jl:127-137
+static void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa, View yb, View dyb,
+                           const RBParams& p, const RBGrads& g, bool accumulate) {
+  const RBShape rs = basic_rb(h, Ca);
+  size_t m = c.ar->mark();
+  RBHidden hid;
+  hid.Y1 = c.ar->f32(rb_hidden_elems(rs));
+  hid.Y2 = c.ar->f32(rb_hidden_elems(rs));
+  hid.G = c.ar->f32(rb_hidden_elems(rs));
+  float* Y3 = c.ar->f32((size_t)h.B * rs.Cout * h.g.px);
+  const int T1 = rs.T1(), T2 = rs.T2();
+  const long long n1 = (long long)h.nh * Ca * T1, n2 = (long long)h.nh * h.nh * T2, n3 = (long long)h.nh * 2 * Ca * T1;
+  RBGrads gw = g;
+  if (accumulate) {  // a later visit of a shared layer: gradients into scratch, then added
+    gw.W1 = c.ar->f32(n1); gw.W2 = c.ar->f32(n2); gw.W3 = c.ar->f32(n3);
+    gw.b1 = c.ar->f32(h.nh); gw.b2 = c.ar->f32(h.nh);
+  }
+  rb_forward(c, rs, xa, view(nullptr, 0), p, hid, Y3);  // recompute (basic.jl:127 -> :112)
+  op_coupling_bwd(c, h.g.px, h.B, Ca, yb, yb, dyb, dyb, Y3, h.low, h.high, h.logdet);  // :114,130-135
+  rb_backward(c, rs, Y3, xa, view(nullptr, 0), p, hid, gw, dxa, dxa.p, dxa.bs, view(nullptr, 0));  // :137
+  if (accumulate) {
+    op_accum(c, n1, gw.W1, g.W1); op_accum(c, n2, gw.W2, g.W2); op_accum(c, n3, gw.W3, g.W3);
+    op_accum(c, h.nh, gw.b1, g.b1); op_accum(c, h.nh, gw.b2, g.b2);
+  }
+  c.ar->release(m);
+}
+
+static void rec_forward(Ctx& c, const HintShape& h, View x, int C, int scale, const HintParams& p, double* ld) {
+  const int Ca = C / 2;
+  View xa = x, xb = sub(x, Ca, h.g.px);
+  INB_CHECK(scale < (int)p.cl.size() + 1, "internal: HINT recursion deeper than the coupling layers");
+  if (C > 4) {
+    rec_forward(c, h, xb, C - Ca, scale + 1, p, ld);
+    basic_forward(c, h, Ca, xa, xb, p.cl[scale - 1], ld);
+    rec_forward(c, h, xa, Ca, scale + 1, p, ld);
+  } else {
+    basic_forward(c, h, Ca, xa, xb, p.cl[scale - 1], ld);
+  }
+}
+static void rec_inverse(Ctx& c, const HintShape& h, View y, int C, int scale, const HintParams& p) {
+  const int Ca = C / 2;
+  View ya = y, yb = sub(y, Ca, h.g.px);
+  if (C > 4) {
+    rec_inverse(c, h, ya, Ca, scale + 1, p);
+    basic_inverse(c, h, Ca, ya, yb, p.cl[scale - 1]);
+    rec_inverse(c, h, yb, C - Ca, scale + 1, p);
+  } else {
+    basic_inverse(c, h, Ca, ya, yb, p.cl[scale - 1]);
+  }
+}
+static void rec_backward(Ctx& c, const HintShape& h, View dy, View y, int C, int scale, const HintParams& p,
+                         const HintGrads& g, std::vector<char>& seen) {
+  const int Ca = C / 2;
+  View ya = y, yb = sub(y, Ca, h.g.px), dya = dy, dyb = sub(dy, Ca, h.g.px);
+  auto coupling = [&] {
+    const bool acc = seen[scale - 1] && !h.shared_last;
+    basic_backward(c, h, Ca, ya, dya, yb, dyb, p.cl[scale - 1], g.cl[scale - 1], acc);
+    seen[scale - 1] = 1;
+  };
+  if (C > 4) {
+    rec_backward(c, h, dya, ya, Ca, scale + 1, p, g, seen);
+    coupling();
+    rec_backward(c, h, dyb, yb, C - Ca, scale + 1, p, g, seen);
+  } else {
+    coupling();
+  }
+}
+
+void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& p, double* ld) {
+  const long long px = h.g.px;
+  const bool full = h.permute == HINT_PERMUTE_FULL;
+  // [ActNorm (actnorm.jl:73)] + C.forward (hint.jl:111-113) in one pass; a plain copy when neither applies
+  if (p.s || full)
+    op_an_hh_fwd(c, px, h.B, h.C, x, y, p.s, p.b, full ? p.v1 : nullptr, full ? p.v2 : nullptr, full ? p.v3 : nullptr,
+                 (p.s && h.logdet) ? ld : nullptr);
+  else
+    op_copy(c, px, h.B, h.C, x, y);
+  if (h.permute == HINT_PERMUTE_LOWER) {  // Xb = C.forward(Xb), :115 (in place: a per-pixel map)
+    const int Ca = h.C / 2;
+    View yb = sub(y, Ca, px);
+    op_an_hh_fwd(c, px, h.B, h.C - Ca, yb, yb, nullptr, nullptr, p.v1, p.v2, p.v3, nullptr);
+  }
+  rec_forward(c, h, y, h.C, 1, p, ld);
+}
+
+void hint_inverse(Ctx& c, const HintShape& h, View y, View x, const HintParams& p) {
+  const long long px = h.g.px;
+  const bool full = h.permute == HINT_PERMUTE_FULL;
+  rec_inverse(c, h, y, h.C, 1, p);
+  if (h.permute == HINT_PERMUTE_LOWER) {  // :193
+    const int Ca = h.C / 2;
+    View yb = sub(y, Ca, px);
+    op_hh_an_inv(c, px, h.B, h.C - Ca, yb, yb, nullptr, nullptr, p.v1, p.v2, p.v3);
+  }
+  if (p.s || full)  // C.inverse (:195-197) [+ ActNorm.inverse]
+    op_hh_an_inv(c, px, h.B, h.C, y, x, p.s, p.b, full ? p.v1 : nullptr, full ? p.v2 : nullptr, full ? p.v3 : nullptr);
+  else if (x.p != y.p)
+    op_copy(c, px, h.B, h.C, y, x);
+}
+
+void hint_backward(Ctx& c, const HintShape& h, View dy, View y, View dx, View x, const HintParams& p,
+                   const HintGrads& g) {
+  const long long px = h.g.px;
+  const bool full = h.permute == HINT_PERMUTE_FULL, lower = h.permute == HINT_PERMUTE_LOWER;
+  size_t m = c.ar->mark();
+  std::vector<char> seen(p.cl.size(), 0);
+  rec_backward(c, h, dy, y, h.C, 1, p, g, seen);
+  const int Cm = lower ? h.C - h.C / 2 : h.C;  // channels the Householder mix acts on
+  double* gram = c.ar->f64((size_t)Cm * Cm + 2 * h.C);
+  double* dsdb = gram + (size_t)Cm * Cm;
+  op_zero(c, gram, ((size_t)Cm * Cm + 2 * h.C) * sizeof(double));
+  if (lower) {  // dXb, Xb = C.inverse((dXb, Xb)), :268
+    View yb = sub(y, h.C / 2, px), dyb = sub(dy, h.C / 2, px);
+    op_hh_an_bwd(c, px, h.B, Cm, dyb, yb, dyb, yb, nullptr, nullptr, p.v1, p.v2, p.v3, gram, nullptr);
+    op_hh_grad_finish(c, Cm, gram, p.v1, p.v2, p.v3, 0, g.v1, g.v2, g.v3);
+  }
+  if (p.s || full) {  // C.inverse((dX, X)) :278 [+ ActNorm.backward, actnorm.jl:100-123]
+    op_hh_an_bwd(c, px, h.B, h.C, dy, y, dx, x, p.s, p.b, full ? p.v1 : nullptr, full ? p.v2 : nullptr,
+                 full ? p.v3 : nullptr, full ? gram : nullptr, p.s ? dsdb : nullptr);
+    if (full) op_hh_grad_finish(c, h.C, gram, p.v1, p.v2, p.v3, 0, g.v1, g.v2, g.v3);
+    if (p.s) op_an_grad_finish(c, h.C, px, dsdb, p.s, h.logdet, g.s, g.b);
+  } else {
+    if (x.p != y.p) op_copy(c, px, h.B, h.C, y, x);
+    if (dx.p != dy.p) op_copy(c, px, h.B, h.C, dy, dx);
+  }
+  c.ar->release(m);
+}
+
+}  // namespace inb

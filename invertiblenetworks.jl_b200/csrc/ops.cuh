@@ -9,6 +9,11 @@ namespace inb {
 void op_squeeze(Ctx& c, const Geo& gin, int B, int C, View in, View out);
 void op_unsqueeze(Ctx& c, const Geo& gout, int B, int Cout, View in, View out);
 void op_copy(Ctx& c, long long px, int B, int C, View in, View out);
+// one-level Haar transform + patch squeeze, 2-D (dimensionality_operations.jl:199-258 with WT.db1: type 0;
+// Haar_squeeze / invHaar_unsqueeze :318-371: type 1).  g, C: the FULL-resolution geometry / channel count.
+void op_haar_squeeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out);
+void op_haar_unsqueeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out);
+void op_accum(Ctx& c, long long n, const float* src, float* dst);
 void op_zero(Ctx& c, void* p, size_t bytes);
 
 // invertible_layer_actnorm.jl:67-72

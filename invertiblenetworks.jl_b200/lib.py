@@ -25,6 +25,20 @@ class GlowDesc(C.Structure):
     ]
 
 
+class HintDesc(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int), ("ny", C.c_int), ("n_in", C.c_int), ("n_hidden", C.c_int),
+        ("L", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("split_scales", C.c_int),
+        ("k1", C.c_int), ("k2", C.c_int), ("p1", C.c_int), ("p2", C.c_int),
+        ("sig_low", C.c_float), ("sig_high", C.c_float),
+        ("squeeze_type", C.c_int), ("shared_grads", C.c_int), ("precision", C.c_int),
+    ]
+
+
+SQUEEZE_TYPES = {"wavelet": 0, "haar": 1}
+PERMUTES = {"none": 0, "full": 1, "lower": 2}
+SHARED_GRADS = {"sum": 0, "last": 1}
+
 P = C.c_void_p      # device pointer / stream / plan
 PP = C.POINTER(C.c_void_p)
 I = C.c_int
@@ -62,6 +76,20 @@ SIGNATURES = {
     "inb_coupling_backward": (I, [I] * 10 + [F, F, I, I, I, P, P, P, PP, PP, P, P, P, P]),
     "inb_squeeze": (I, [I, I, I, I, I, I, P, P, P]),
     "inb_unsqueeze": (I, [I, I, I, I, I, I, P, P, P]),
+    "inb_haar_squeeze": (I, [I, I, I, I, I, P, P, P]),
+    "inb_haar_unsqueeze": (I, [I, I, I, I, I, P, P, P]),
+    "inb_hint_depth": (I, [I]),
+    "inb_hint_coupling_forward": (I, [I] * 9 + [F, F, I, I, P, PP, P, P, P]),
+    "inb_hint_coupling_inverse": (I, [I] * 9 + [F, F, I, I, P, PP, P, P]),
+    "inb_hint_coupling_backward": (I, [I] * 9 + [F, F, I, I, I, I, P, P, PP, PP, P, P, P]),
+    "inb_hint_plan_create": (I, [C.POINTER(HintDesc), C.POINTER(P)]),
+    "inb_hint_plan_destroy": (I, [P]),
+    "inb_hint_num_params": (I, [P]),
+    "inb_hint_param_numel": (I, [P, I, C.POINTER(LL)]),
+    "inb_hint_workspace_bytes": (LL, [P]),
+    "inb_hint_forward": (I, [P, I, P, PP, P, P, I, P]),
+    "inb_hint_inverse": (I, [P, I, P, PP, P, P]),
+    "inb_hint_backward": (I, [P, I, P, P, PP, PP, P, P, P]),
     "inb_nll_grad": (I, [LL, I, P, P, P, P]),
     "inb_adam_update": (I, [LL, P, P, P, P, F, F, F, F, F, F, P]),
     "inb_launch_count": (LL, []),
