@@ -106,15 +106,8 @@ struct ScaleInfo {
   int kc;       // channels that continue after the split (== C when no split)
 };
 
-struct inb_plan {
-  inb_glow_desc d;
-  bool cond;
-  std::vector<ScaleInfo> sc;
-  Geo g0;  // input geometry
-  Arena ar;
-  size_t persist = 0;  // bytes at the start of the arena that survive calls (logdet accumulator)
-  size_t need = 0;     // workspace bytes (sizing pass at plan creation)
-  double* ld = nullptr;
+// graph-replay state shared by the network plans (run_graphed)
+struct GraphCache {
   // CUDA graphs of the network-level calls (slot 0 forward, 1 inverse, 2 backward): a call with the same
   // pointers and batch as the captured one replays ~1500 launches with a single cudaGraphLaunch
   // (a caller's allocator typically cycles through a few addresses for its outputs: kGraphWays entries per
@@ -133,6 +126,23 @@ struct inb_plan {
   uint32_t graph_hist[3] = {0, 0, 0};
   long long graph_captures = 0, graph_replays = 0, graph_direct = 0;
   cudaStream_t capture_stream = nullptr;
+  void destroy_graphs() {
+    for (auto& slot : graphs)
+      for (auto& g : slot)
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (capture_stream) { cudaStreamDestroy(capture_stream); capture_stream = nullptr; }
+  }
+};
+
+struct inb_plan : GraphCache {
+  inb_glow_desc d;
+  bool cond;
+  std::vector<ScaleInfo> sc;
+  Geo g0;  // input geometry
+  Arena ar;
+  size_t persist = 0;  // bytes at the start of the arena that survive calls (logdet accumulator)
+  size_t need = 0;     // workspace bytes (sizing pass at plan creation)
+  double* ld = nullptr;
   SideLane lane;
 };
 
@@ -518,8 +528,8 @@ static bool graphs_enabled() {
 // private stream (nothing executes during capture), instantiate, launch on the caller's stream; later calls
 // with the same key: one cudaGraphLaunch.  Falls back to direct launches while profiling, inside a caller's own
 // capture, or with INB_GRAPHS=0.
-template <class F>
-static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& enqueue) {
+template <class Plan, class F>
+static void run_graphed(Plan* p, int slot, uint64_t key, void* stream, F&& enqueue) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
@@ -529,7 +539,7 @@ static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& e
     enqueue(c);
     return;
   }
-  inb_plan::GraphSlot* gp = nullptr;
+  GraphCache::GraphSlot* gp = nullptr;
   bool full = true;
   for (auto& w : p->graphs[slot]) {
     if (w.exec && w.key == key) gp = &w;
@@ -548,7 +558,7 @@ static void run_graphed(inb_plan* p, int slot, uint64_t key, void* stream, F&& e
     for (auto& w : p->graphs[slot])
       if (w.used < gp->used) gp = &w;
   }
-  inb_plan::GraphSlot& g = *gp;
+  GraphCache::GraphSlot& g = *gp;
   g.used = ++p->graph_clock;
   if (g.exec == nullptr || g.key != key) {
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
@@ -627,10 +637,7 @@ int inb_glow_plan_create(const inb_glow_desc* desc, inb_plan** out) {
 int inb_glow_plan_destroy(inb_plan* p) {
   return guarded([&] {
     if (!p) return;
-    for (auto& slot : p->graphs)
-      for (auto& g : slot)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
-    if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
+    p->destroy_graphs();
     if (p->lane.st) cudaStreamDestroy(p->lane.st);
     for (int i = 0; i < p->lane.nev; ++i) cudaEventDestroy(p->lane.ev[i]);
     delete[] p->lane.ev;
@@ -1119,7 +1126,7 @@ struct HintScale {
   int depth;
   int pbase; // index of CL[i,1]'s first parameter
 };
-struct inb_hint_plan {
+struct inb_hint_plan : GraphCache {
   inb_hint_desc d;
   Geo g0;
   std::vector<HintScale> sc;
@@ -1238,7 +1245,7 @@ static void hint_drive_reverse(inb_hint_plan* p, Ctx& c, int B, bool grads, cons
   c.ar->release(m);
 }
 
-static Ctx hint_call_ctx(inb_hint_plan* p, void* stream) {
+static Ctx call_ctx(inb_hint_plan* p, void* stream) {
   if (!p->ar.base) {
     void* base = nullptr;
     cudaError_t e = cudaMalloc(&base, p->need);
@@ -1252,6 +1259,15 @@ static Ctx hint_call_ctx(inb_hint_plan* p, void* stream) {
   }
   p->ar.off = p->persist;
   return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
+}
+static uint64_t hint_key(const inb_hint_plan* p, int batch, std::initializer_list<const void*> ptrs,
+                         float* const* params, float* const* grads) {
+  uint64_t h = mix(0x48494e54ull, (uint64_t)batch);
+  for (const void* q : ptrs) h = mix(h, (uint64_t)(uintptr_t)q);
+  for (int i = 0; i < p->nparams; ++i) h = mix(h, (uint64_t)(uintptr_t)params[i]);
+  if (grads)
+    for (int i = 0; i < p->nparams; ++i) h = mix(h, (uint64_t)(uintptr_t)grads[i]);
+  return h | 1ull;
 }
 static void hint_check_call(inb_hint_plan* p, int batch) {
   INB_CHECK(p != nullptr, "null plan");
@@ -1305,6 +1321,7 @@ int inb_hint_plan_create(const inb_hint_desc* d, inb_hint_plan** out) {
 int inb_hint_plan_destroy(inb_hint_plan* p) {
   return guarded([&] {
     if (!p) return;
+    p->destroy_graphs();
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;
   });
@@ -1341,16 +1358,21 @@ int inb_hint_forward(inb_hint_plan* p, int batch, const float* X, float* const* 
   return guarded([&] {
     hint_check_call(p, batch);
     INB_CHECK(X && params && Z, "null tensor argument");
-    Ctx c = hint_call_ctx(p, stream);
-    hint_drive_forward(p, c, batch, X, params, Z, logdet, init_actnorm);
+    if (init_actnorm) {  // data-dependent initialisation: never replayed
+      Ctx c = call_ctx(p, stream);
+      hint_drive_forward(p, c, batch, X, params, Z, logdet, 1);
+      return;
+    }
+    run_graphed(p, 0, hint_key(p, batch, {X, Z, logdet}, params, nullptr), stream,
+                [&](Ctx& c) { hint_drive_forward(p, c, batch, X, params, Z, logdet, 0); });
   });
 }
 int inb_hint_inverse(inb_hint_plan* p, int batch, const float* Z, float* const* params, float* X, void* stream) {
   return guarded([&] {
     hint_check_call(p, batch);
     INB_CHECK(X && params && Z, "null tensor argument");
-    Ctx c = hint_call_ctx(p, stream);
-    hint_drive_reverse(p, c, batch, false, nullptr, Z, params, nullptr, nullptr, X);
+    run_graphed(p, 1, hint_key(p, batch, {Z, X}, params, nullptr), stream,
+                [&](Ctx& c) { hint_drive_reverse(p, c, batch, false, nullptr, Z, params, nullptr, nullptr, X); });
   });
 }
 int inb_hint_backward(inb_hint_plan* p, int batch, const float* dZ, const float* Z, float* const* params,
@@ -1358,8 +1380,8 @@ int inb_hint_backward(inb_hint_plan* p, int batch, const float* dZ, const float*
   return guarded([&] {
     hint_check_call(p, batch);
     INB_CHECK(dZ && Z && params && grads && dX && X, "null tensor argument");
-    Ctx c = hint_call_ctx(p, stream);
-    hint_drive_reverse(p, c, batch, true, dZ, Z, params, grads, dX, X);
+    run_graphed(p, 2, hint_key(p, batch, {dZ, Z, dX, X}, params, grads), stream,
+                [&](Ctx& c) { hint_drive_reverse(p, c, batch, true, dZ, Z, params, grads, dX, X); });
   });
 }
 

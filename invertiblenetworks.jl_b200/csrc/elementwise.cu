@@ -5,6 +5,7 @@
 // pixels and all C channels of them in registers: every global access of a warp is a contiguous
 // 128*V-byte run per channel (coalesced, vectorised), each element is read once and written once.
 #include "ops.cuh"
+#include <algorithm>
 
 namespace inb {
 
@@ -195,15 +196,32 @@ void op_haar_unsqueeze(Ctx& c, const Geo& g, int B, int C, int type, View in, Vi
   INB_CUDA(cudaGetLastError());
 }
 
-// dst += src (gradients of a coupling layer that the HINT recursion visits more than once)
-__global__ void k_accum(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+// dst[i] += src[i] for up to five (src, dst, n) pairs in one launch (grid row = pair): the five ResidualBlock gradients
+// of a coupling layer that the HINT recursion visits more than once
+struct AccumArgs {
+  const float* src[5];
+  float* dst[5];
+  long long n[5];
+};
+__global__ void k_accum(const AccumArgs a) {
+  const float* __restrict__ src = a.src[blockIdx.y];
+  float* __restrict__ dst = a.dst[blockIdx.y];
+  const long long n = a.n[blockIdx.y];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] += src[i];
 }
-void op_accum(Ctx& c, long long n, const float* src, float* dst) {
-  if (c.dry() || n == 0) return;
-  Prof pf(c, F_MISC, 1, 0, 12.0 * n);
-  k_accum<<<grid_for(n, 256), 256, 0, c.st>>>(src, dst, n);
+void op_accum(Ctx& c, int npairs, const float* const* src, float* const* dst, const long long* n) {
+  INB_CHECK(npairs >= 1 && npairs <= 5, "op_accum: 1 to 5 pairs");
+  if (c.dry()) return;
+  AccumArgs a{};
+  long long nmax = 0, tot = 0;
+  for (int i = 0; i < npairs; ++i) {
+    a.src[i] = src[i]; a.dst[i] = dst[i]; a.n[i] = n[i];
+    nmax = std::max(nmax, n[i]);
+    tot += n[i];
+  }
+  Prof pf(c, F_MISC, 1, 0, 12.0 * tot);
+  k_accum<<<dim3(grid_for(nmax, 256, 2), npairs, 1), 256, 0, c.st>>>(a);
   INB_CUDA(cudaGetLastError());
 }
 

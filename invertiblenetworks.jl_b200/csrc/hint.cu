@@ -82,8 +82,10 @@ static void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa
   op_coupling_bwd(c, h.g.px, h.B, Ca, yb, yb, dyb, dyb, Y3, h.low, h.high, h.logdet);  // :114,130-135
   rb_backward(c, rs, Y3, xa, view(nullptr, 0), p, hid, gw, dxa, dxa.p, dxa.bs, view(nullptr, 0));  // :137
   if (accumulate) {
-    op_accum(c, n1, gw.W1, g.W1); op_accum(c, n2, gw.W2, g.W2); op_accum(c, n3, gw.W3, g.W3);
-    op_accum(c, h.nh, gw.b1, g.b1); op_accum(c, h.nh, gw.b2, g.b2);
+    const float* src[5] = {gw.W1, gw.W2, gw.W3, gw.b1, gw.b2};
+    float* dst[5] = {g.W1, g.W2, g.W3, g.b1, g.b2};
+    const long long n[5] = {n1, n2, n3, h.nh, h.nh};
+    op_accum(c, 5, src, dst, n);
   }
   c.ar->release(m);
 }

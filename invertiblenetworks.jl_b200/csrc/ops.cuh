@@ -13,7 +13,8 @@ void op_copy(Ctx& c, long long px, int B, int C, View in, View out);
 // Haar_squeeze / invHaar_unsqueeze :318-371: type 1).  g, C: the FULL-resolution geometry / channel count.
 void op_haar_squeeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out);
 void op_haar_unsqueeze(Ctx& c, const Geo& g, int B, int C, int type, View in, View out);
-void op_accum(Ctx& c, long long n, const float* src, float* dst);
+// dst[i] += src[i] for up to five pairs in one launch
+void op_accum(Ctx& c, int npairs, const float* const* src, float* const* dst, const long long* n);
 void op_zero(Ctx& c, void* p, size_t bytes);
 
 // invertible_layer_actnorm.jl:67-72

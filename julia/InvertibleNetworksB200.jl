@@ -13,7 +13,7 @@ module InvertibleNetworksB200
 
 using CUDA
 using InvertibleNetworks
-import InvertibleNetworks: forward, inverse, backward, NetworkGlow, NetworkConditionalGlow, ActNorm,
+import InvertibleNetworks: forward, inverse, backward, NetworkGlow, NetworkConditionalGlow, NetworkMultiScaleHINT, ActNorm,
                            Conv1x1, CouplingLayerGlow, ResidualBlock, get_params, Parameter
 
 const LIB = get(ENV, "INB200_LIB", joinpath(@__DIR__, "..", "invertiblenetworks.jl_b200", "libinb200.so"))
@@ -234,6 +234,92 @@ function InvertibleNetworks.squeeze(X::CuArray{Float32,N}; pattern="column") whe
     check(ccall((:inb_squeeze, LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
                 nd, size(X, 1), size(X, 2), nd == 3 ? size(X, 3) : 1, size(X, N), size(X, N - 1), dptr(X), dptr(Y), stream()))
     return Y
+end
+
+# ---------------------------------------------------------------- HINT family (SURVEY 8f rank 3)
+# mirrors `inb_hint_desc`
+struct HintDesc
+    nx::Cint; ny::Cint; n_in::Cint; n_hidden::Cint; L::Cint; K::Cint; batch::Cint; split_scales::Cint
+    k1::Cint; k2::Cint; p1::Cint; p2::Cint
+    sig_low::Cfloat; sig_high::Cfloat
+    squeeze_type::Cint; shared_grads::Cint; precision::Cint
+end
+# 0 = sum the gradients of coupling layers the recursion visits several times (the true gradient, what the
+# reference's set_grad=false path returns, invertible_layer_hint.jl:222); 1 = keep the last visit only (what its
+# set_grad=true path leaves in .grad, layer_residual_block.jl:168-172)
+const HINT_SHARED_GRADS = Ref{Cint}(parse(Cint, get(ENV, "INB200_HINT_SHARED_GRADS", "0")))
+const HINT_PLANS = IdDict{Any,Tuple{Any,Ptr{Cvoid}}}()
+
+function hint_plan_for(H::NetworkMultiScaleHINT, X::CuArray{Float32,4})
+    key = (size(X, 1), size(X, 2), size(X, 4))
+    haskey(HINT_PLANS, H) && HINT_PLANS[H][1] == key && return HINT_PLANS[H][2]
+    haskey(HINT_PLANS, H) && ccall((:inb_hint_plan_destroy, LIB), Cint, (Ptr{Cvoid},), HINT_PLANS[H][2])
+    rb = H.CL[1, 1].CL[1].RB
+    k1, k2 = size(rb.W1.data, 1), size(rb.W2.data, 1)
+    act = H.CL[1, 1].CL[1].activation
+    desc = HintDesc(size(X, 1), size(X, 2), size(X, 3), size(rb.W2.data, 4), H.L, H.K, size(X, 4), H.split_scales,
+                    k1, k2, (k1 - 1) ÷ 2, (k2 - 1) ÷ 2, act.low, act.high, 0, HINT_SHARED_GRADS[], PRECISION[])
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:inb_hint_plan_create, LIB), Cint, (Ref{HintDesc}, Ref{Ptr{Cvoid}}), desc, p))
+    HINT_PLANS[H] = (key, p[])
+    return p[]
+end
+
+# replaces src/networks/invertible_network_hint_multiscale.jl:98-117
+function forward(X::CuArray{Float32,4}, H::NetworkMultiScaleHINT)
+    plan = hint_plan_for(H, X)
+    init = ensure_actnorm!(H, Float32, CuArray)
+    f = 2^H.L
+    Z = H.split_scales ? CUDA.zeros(Float32, length(X)) :
+        CUDA.zeros(Float32, size(X, 1) ÷ f, size(X, 2) ÷ f, size(X, 3) * 4^H.L, size(X, 4))
+    ld = CUDA.zeros(Float32, 1)
+    check(ccall((:inb_hint_forward, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Ptr{Cvoid}),
+                plan, size(X, 4), dptr(X), ptr_table(get_params(H), :data), dptr(Z), dptr(ld), init, stream()))
+    HINT_INPUT[H] = size(X)   # stands in for H.X_dims (:111)
+    return Z, Array(ld)[1]
+end
+const HINT_INPUT = IdDict{Any,Any}()
+hint_input_shape(H, Z) = haskey(HINT_INPUT, H) && prod(HINT_INPUT[H]) == length(Z) ? HINT_INPUT[H] :
+    (size(Z, 1) * 2^H.L, size(Z, 2) * 2^H.L, size(Z, 3) ÷ 4^H.L, size(Z, 4))
+
+# replaces :120-133
+function inverse(Z::CuArray{Float32}, H::NetworkMultiScaleHINT)
+    X = CUDA.zeros(Float32, hint_input_shape(H, Z)...)
+    plan = hint_plan_for(H, X)
+    check(ccall((:inb_hint_inverse, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cvoid}),
+                plan, size(X, 4), dptr(Z), ptr_table(get_params(H), :data), dptr(X), stream()))
+    return X
+end
+
+# replaces :136-174 (set_grad = true; the Jacobian paths stay on the reference)
+function backward(ΔZ::CuArray{Float32}, Z::CuArray{Float32}, H::NetworkMultiScaleHINT; set_grad::Bool=true)
+    set_grad || return invoke(backward, Tuple{AbstractArray{Float32},AbstractArray{Float32},NetworkMultiScaleHINT},
+                              ΔZ, Z, H; set_grad=false)
+    shape = hint_input_shape(H, Z)
+    X, ΔX = CUDA.zeros(Float32, shape...), CUDA.zeros(Float32, shape...)
+    plan = hint_plan_for(H, X)
+    ps = get_params(H)
+    fresh = [CUDA.zeros(Float32, size(p.data)) for p in ps]
+    check(ccall((:inb_hint_backward, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                plan, shape[end], dptr(ΔZ), dptr(Z), ptr_table(ps, :data), Ptr{Cfloat}[dptr(g) for g in fresh],
+                dptr(ΔX), dptr(X), stream()))
+    assign_grads!(H, ps, fresh)   # H.CL[i,j].C is the Conv1x1 whose gradients accumulate (conv1x1.jl:237-239)
+    return ΔX, X
+end
+
+# replaces wavelet_squeeze / wavelet_unsqueeze with type = WT.db1 and Haar_squeeze / invHaar_unsqueeze
+# (src/utils/dimensionality_operations.jl:199-258, 318-371), 4-D tensors
+for (fn, sym, ty, up) in ((:wavelet_squeeze, :inb_haar_squeeze, 0, false), (:wavelet_unsqueeze, :inb_haar_unsqueeze, 0, true),
+                          (:Haar_squeeze, :inb_haar_squeeze, 1, false), (:invHaar_unsqueeze, :inb_haar_unsqueeze, 1, true))
+    @eval function InvertibleNetworks.$fn(X::CuArray{Float32,4})
+        Y = $up ? CUDA.zeros(Float32, 2size(X, 1), 2size(X, 2), size(X, 3) ÷ 4, size(X, 4)) :
+                  CUDA.zeros(Float32, size(X, 1) ÷ 2, size(X, 2) ÷ 2, 4size(X, 3), size(X, 4))
+        check(ccall(($(QuoteNode(sym)), LIB), Cint, (Cint, Cint, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                    size(X, 1), size(X, 2), size(X, 4), size(X, 3), $ty, dptr(X), dptr(Y), stream()))
+        return Y
+    end
 end
 
 # Optional replacement of the `for p in get_params(G); update!(opt, p.data, p.grad); end` loop with Flux.ADAM

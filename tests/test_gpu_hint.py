@@ -127,12 +127,17 @@ def run_hint_network(n_in, nh, L, K, shape, *, split, k2=1, squeezer="wavelet", 
     dX, Xr = net.backward(g(dZ), g(Zin))
     with FragileUnits(fragile_thr) as fr:
         dX64, X64 = N64.backward(dZ.double(), Zin.double())
-    assert rel(Xr, X64) < max(tol_out, inv_tol)
-    assert_grad_close(dX, dX64, tol_out, fr, "dX")
-    ps, qs = net.get_params(), N64.get_params()
+    # two columns: the CUDA path against truth beside the float32 oracle against truth.  The sigmoid scale
+    # of CouplingLayerBasic reaches down to 0 (SigmoidLayer(), low = 0), so inverting 2^depth couplings per layer
+    # amplifies float32 rounding - the reference's own bound on the recomputed X is rtol 1f-3 (:30); the CUDA path
+    # must stay within 3x of what the reference's float32 arithmetic shows on the same numbers.
+    dX32, X32 = N32.backward(dZ, Zin)
+    assert rel(Xr, X64) < max(tol_out, 3 * rel(X32, X64))
+    assert_grad_close(dX, dX64, max(tol_out, 3 * rel(dX32, dX64)), fr, "dX")
+    ps, qs, q32 = net.get_params(), N64.get_params(), N32.get_params()
     assert len(ps) == len(qs) and all(p.grad is not None for p in ps)
-    for i, (p, q) in enumerate(zip(ps, qs)):
-        assert_grad_close(p.grad, q.grad, tol_grad, fr, f"gradient {i}")
+    for i, (p, q, r) in enumerate(zip(ps, qs, q32)):
+        assert_grad_close(p.grad, q.grad, max(tol_grad, 3 * rel(r.grad, q.grad)), fr, f"gradient {i}")
     inb200.clear_grad(net)
     assert all(p.grad is None for p in net.get_params())
 
@@ -187,12 +192,15 @@ def test_multiscale_hint_cfg4_full_size_properties():
     s, b = net.get_params()[0].data, net.get_params()[1].data
     Yn = Y * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
     assert Yn.mean(dim=(0, 2, 3)).abs().max() < 1e-4 and (Yn.var(dim=(0, 2, 3)) - 1).abs().max() < 1e-3
-    # directional derivative of the loss along dX (Taylor test of :46-66 in one step, float32)
-    def loss(Xx):
-        Zz, l = net.forward(Xx)
-        return (0.5 * torch.sum(Zz.double() ** 2) / B - l.double()).item()
-    d = torch.randn_like(X)
-    h = 1e-2
-    fd = (loss(X + h * d) - loss(X - h * d)) / (2 * h)
-    an = torch.sum(dX.double() * d.double()).item()
-    assert abs(fd - an) < 2e-2 * abs(an) + 1e-2
+    # adjoint test of the backward pass at full size: backward is affine in dZ, dX(dZ) = J' dZ + c (c = the logdet
+    # gradient), so <dX(dZ) - dX(0), d> = <dZ, J d> with J d from a central difference of the forward pass.  (A Taylor
+    # test of the scalar loss, :46-66, is limited here by the float32 logdet: 1e-7 * |logdet| / h.)
+    dZr, d = torch.randn_like(Z), torch.randn_like(X)
+    lhs = torch.sum((net.backward(dZr, Z)[0] - net.backward(0 * dZr, Z)[0]).double() * d.double()).item()
+    h = 1e-3
+    Jd = (net.forward(X + h * d)[0].double() - net.forward(X - h * d)[0].double()) / (2 * h)
+    rhs = torch.sum(dZr.double() * Jd).item()
+    assert abs(lhs - rhs) < 1e-2 * abs(rhs), (lhs, rhs)
+    # and it is linear in dZ beyond the constant: dX(2 dZ) - dX(dZ) = dX(dZ) - dX(0)
+    a, b, c0 = net.backward(2 * dZr, Z)[0], net.backward(dZr, Z)[0], net.backward(0 * dZr, Z)[0]
+    assert rel(a - b, b - c0) < 1e-4
