@@ -491,12 +491,21 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
     p->lane.pool_bytes = (size_t)steps * ((((size_t)cmax * cmax + 2 * cmax) * sizeof(double) + 255) & ~size_t(255));
     INB_CUDA(cudaMalloc(&p->lane.pool, p->lane.pool_bytes));
     INB_CUDA(cudaStreamCreateWithFlags(&p->lane.st, cudaStreamNonBlocking));
+    static const bool no_wlanes = [] { const char* e = getenv("INB_WGRAD_LANES"); return e && e[0] == '0'; }();
+    if (!no_wlanes) {
+      p->lane.nwev = 3 * steps;
+      p->lane.wev = new cudaEvent_t[p->lane.nwev];
+      for (int i = 0; i < p->lane.nwev; ++i) INB_CUDA(cudaEventCreateWithFlags(&p->lane.wev[i], cudaEventDisableTiming));
+      INB_CUDA(cudaStreamCreateWithFlags(&p->lane.wst[0], cudaStreamNonBlocking));
+      INB_CUDA(cudaStreamCreateWithFlags(&p->lane.wst[1], cudaStreamNonBlocking));
+    }
   }
   Ctx c{(cudaStream_t)stream, &p->ar, p->d.precision};
   if (p->lane.st) {
     p->lane.next = 0;
     p->lane.pool_off = 0;
     p->lane.used = false;
+    p->lane.wnext = 0;
     c.lane = &p->lane;
   }
   return c;
@@ -642,6 +651,10 @@ int inb_glow_plan_destroy(inb_plan* p) {
     for (int i = 0; i < p->lane.nev; ++i) cudaEventDestroy(p->lane.ev[i]);
     delete[] p->lane.ev;
     if (p->lane.pool) cudaFree(p->lane.pool);
+    for (int i = 0; i < 2; ++i)
+      if (p->lane.wst[i]) cudaStreamDestroy(p->lane.wst[i]);
+    for (int i = 0; i < p->lane.nwev; ++i) cudaEventDestroy(p->lane.wev[i]);
+    delete[] p->lane.wev;
     if (p->ar.base) cudaFree(p->ar.base);
     delete p;
   });

@@ -91,6 +91,11 @@ struct SideLane {
   char* pool = nullptr;
   size_t pool_bytes = 0, pool_off = 0;
   bool used = false;
+  // two more streams for the weight gradients of a block when each of them fills less than half of the SMs (small batch
+  // shards, coarse scales): the three split-K kernels then run side by side (op_wgrad2_tc_multi)
+  cudaStream_t wst[2] = {nullptr, nullptr};
+  cudaEvent_t* wev = nullptr;
+  int nwev = 0, wnext = 0;
   void* take(size_t n) {
     size_t a = (pool_off + 255) & ~size_t(255);
     if (!pool || a + n > pool_bytes || next + 2 > nev) return nullptr;

@@ -315,7 +315,31 @@ void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n) {
   size_t mk = c.ar->mark();
   WgradReduceArgs ra{};
   long long outs = 0;
-  for (int i = 0; i < n; ++i) outs = std::max(outs, wgrad2_launch(c, specs[i], ra.d[i]));
+  // Small pixel counts (a batch shard of 8, the coarse scales): a split-K kernel then occupies at most half of the SMs
+  // (>= 512 pixels per CTA) and is latency-bound, so the three of a block run side by side on three streams - parallel
+  // branches of the captured graph - and the reduction follows their join.
+  SideLane* L = c.lane;
+  const bool side_by_side = !c.dry() && n == 3 && L && L->wst[0] && L->wnext + 3 <= L->nwev &&
+                            specs[0].M / (kWgPB * 16) <= 74 && specs[0].M == specs[1].M && specs[0].M == specs[2].M;
+  if (side_by_side) {
+    cudaEvent_t ef = L->wev[L->wnext], e1 = L->wev[L->wnext + 1], e2 = L->wev[L->wnext + 2];
+    L->wnext += 3;
+    INB_CUDA(cudaEventRecord(ef, c.st));
+    INB_CUDA(cudaStreamWaitEvent(L->wst[0], ef, 0));
+    INB_CUDA(cudaStreamWaitEvent(L->wst[1], ef, 0));
+    Ctx c1 = c, c2 = c;
+    c1.st = L->wst[0];
+    c2.st = L->wst[1];
+    outs = std::max(outs, wgrad2_launch(c, specs[0], ra.d[0]));
+    outs = std::max(outs, wgrad2_launch(c1, specs[1], ra.d[1]));
+    outs = std::max(outs, wgrad2_launch(c2, specs[2], ra.d[2]));
+    INB_CUDA(cudaEventRecord(e1, L->wst[0]));
+    INB_CUDA(cudaEventRecord(e2, L->wst[1]));
+    INB_CUDA(cudaStreamWaitEvent(c.st, e1, 0));
+    INB_CUDA(cudaStreamWaitEvent(c.st, e2, 0));
+  } else {
+    for (int i = 0; i < n; ++i) outs = std::max(outs, wgrad2_launch(c, specs[i], ra.d[i]));
+  }
   if (!c.dry()) {
     Prof pf(c, F_WGRAD_TC, 1, 0, 0);
     dim3 grid((unsigned)std::min<long long>(cdiv(outs, 64), 148 * 4), (unsigned)n, 1);
