@@ -319,6 +319,10 @@ static void drive_forward(inb_plan* p, Ctx& c, int B, const float* X, const floa
   c.ar->release(m);
 }
 
+static bool wgrad_defer_enabled() {
+  static const bool on = [] { const char* e = getenv("INB_WGRAD_DEFER"); return !(e && e[0] == '0'); }();
+  return on;
+}
 // inverse (grads == false) and backward (grads == true) share the reverse sweep
 static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* dZ, const float* Z,
                           const float* ZC, float* const* prm, float* const* gr, float* dX, float* X,
@@ -383,6 +387,20 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
       pre_f = rb_prepack_chain(c, f.rb(), rbp.data(), d.K, 0, packs_f.data());
       if (grads) pre_b = rb_prepack_chain(c, f.rb(), rbp.data(), d.K, 1, packs_b.data());
     }
+    // Small shards / coarse scales (a weight-gradient kernel fills at most half of the SMs): the weight gradients of a
+    // step leave the main stream and overlap the next step.  The steps then alternate between two workspace regions
+    // (the second starts `foot` bytes above the first), and a region is reused only after its gradients are done.
+    size_t foot = 0;
+    if (grads && pre_b && (long long)B * s.g.px / 512 <= 74 && wgrad_defer_enabled()) {
+      Arena tmp;
+      tmp.dry = true;
+      Ctx tc{nullptr, &tmp, c.prec};
+      FlowParams fp0 = flow_params(p, i, 0, nullptr);
+      fp0.rb.pre[0] = &packs_f[0];
+      fp0.rb.pre[1] = &packs_b[0];
+      flow_backward(tc, f, dy, y, dy, y, cond, dcond, fp0, FlowGrads{});
+      foot = (tmp.peak + 1023) & ~size_t(1023);
+    }
     for (int j = d.K - 1; j >= 0; --j) {
       FlowParams fp = flow_params(p, i, j, prm);
       if (pre_f) fp.rb.pre[0] = &packs_f[j];
@@ -395,10 +413,26 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
       }
       if (grads) {
         FlowGrads fg = flow_grads(p, i, j, gr);
-        flow_backward(c, f, dy, y, dxo, xo, cond, dcond, fp, fg);  // :173-174
+        const size_t mstep = c.ar->mark();
+        Ctx sc = c;
+        if (foot) {
+          const int q = (d.K - 1 - j) & 1;
+          if (q) c.ar->alloc_bytes(foot);
+          if (c.lane && !c.dry()) {
+            c.lane->wait_deferred(c.st, q);
+            c.lane->wparity = q;
+            sc.wg_defer = true;
+          }
+        }
+        flow_backward(sc, f, dy, y, dxo, xo, cond, dcond, fp, fg);  // :173-174
+        c.ar->release(mstep);
       } else {
         flow_inverse(c, f, y, xo, cond, fp);  // :139-140
       }
+    }
+    if (foot && c.lane && !c.dry()) {  // the scale's workspace is recycled below
+      c.lane->wait_deferred(c.st, 0);
+      c.lane->wait_deferred(c.st, 1);
     }
     c.ar->release(mpack);
     if (d.split_scales) {  // :186-187 unsqueeze
@@ -493,11 +527,12 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
     INB_CUDA(cudaStreamCreateWithFlags(&p->lane.st, cudaStreamNonBlocking));
     static const bool no_wlanes = [] { const char* e = getenv("INB_WGRAD_LANES"); return e && e[0] == '0'; }();
     if (!no_wlanes) {
-      p->lane.nwev = 3 * steps;
+      p->lane.nwev = 4 * steps;
       p->lane.wev = new cudaEvent_t[p->lane.nwev];
       for (int i = 0; i < p->lane.nwev; ++i) INB_CUDA(cudaEventCreateWithFlags(&p->lane.wev[i], cudaEventDisableTiming));
       INB_CUDA(cudaStreamCreateWithFlags(&p->lane.wst[0], cudaStreamNonBlocking));
       INB_CUDA(cudaStreamCreateWithFlags(&p->lane.wst[1], cudaStreamNonBlocking));
+      INB_CUDA(cudaStreamCreateWithFlags(&p->lane.wst[2], cudaStreamNonBlocking));
     }
   }
   Ctx c{(cudaStream_t)stream, &p->ar, p->d.precision};
@@ -506,6 +541,8 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
     p->lane.pool_off = 0;
     p->lane.used = false;
     p->lane.wnext = 0;
+    p->lane.wparity = 0;
+    p->lane.wpending[0] = p->lane.wpending[1] = false;
     c.lane = &p->lane;
   }
   return c;
@@ -651,7 +688,7 @@ int inb_glow_plan_destroy(inb_plan* p) {
     for (int i = 0; i < p->lane.nev; ++i) cudaEventDestroy(p->lane.ev[i]);
     delete[] p->lane.ev;
     if (p->lane.pool) cudaFree(p->lane.pool);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
       if (p->lane.wst[i]) cudaStreamDestroy(p->lane.wst[i]);
     for (int i = 0; i < p->lane.nwev; ++i) cudaEventDestroy(p->lane.wev[i]);
     delete[] p->lane.wev;

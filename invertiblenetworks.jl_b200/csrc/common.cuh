@@ -93,9 +93,19 @@ struct SideLane {
   bool used = false;
   // two more streams for the weight gradients of a block when each of them fills less than half of the SMs (small batch
   // shards, coarse scales): the three split-K kernels then run side by side (op_wgrad2_tc_multi)
-  cudaStream_t wst[2] = {nullptr, nullptr};
+  cudaStream_t wst[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t* wev = nullptr;
   int nwev = 0, wnext = 0;
+  // deferred mode (Ctx::wg_defer): all three kernels and their reduction leave the main stream and overlap the NEXT
+  // flow step; the steps alternate between two workspace regions (wparity) and the main stream waits for wdone[q]
+  // before a region is written again (drive_reverse)
+  int wparity = 0;
+  cudaEvent_t wdone[2] = {nullptr, nullptr};
+  bool wpending[2] = {false, false};
+  void wait_deferred(cudaStream_t main, int q) {
+    if (wpending[q]) INB_CUDA(cudaStreamWaitEvent(main, wdone[q], 0));
+    wpending[q] = false;
+  }
   void* take(size_t n) {
     size_t a = (pool_off + 255) & ~size_t(255);
     if (!pool || a + n > pool_bytes || next + 2 > nev) return nullptr;
@@ -124,6 +134,7 @@ struct Ctx {
   Arena* ar;
   int prec;  // INB_PREC_*
   SideLane* lane = nullptr;
+  bool wg_defer = false;  // weight gradients of this flow step may leave the main stream (SideLane::wparity)
   bool dry() const { return ar->dry; }
 };
 

@@ -321,6 +321,33 @@ void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n) {
   SideLane* L = c.lane;
   const bool side_by_side = !c.dry() && n == 3 && L && L->wst[0] && L->wnext + 3 <= L->nwev &&
                             specs[0].M / (kWgPB * 16) <= 74 && specs[0].M == specs[1].M && specs[0].M == specs[2].M;
+  if (side_by_side && c.wg_defer && L->wst[2] && L->wnext + 4 <= L->nwev) {
+    // all three off the main stream; nothing on the main stream waits for them before the region is reused
+    cudaEvent_t ef = L->wev[L->wnext], e1 = L->wev[L->wnext + 1], e2 = L->wev[L->wnext + 2], ed = L->wev[L->wnext + 3];
+    L->wnext += 4;
+    INB_CUDA(cudaEventRecord(ef, c.st));
+    Ctx cc[3] = {c, c, c};
+    for (int i = 0; i < 3; ++i) {
+      cc[i].st = L->wst[i];
+      INB_CUDA(cudaStreamWaitEvent(L->wst[i], ef, 0));
+      outs = std::max(outs, wgrad2_launch(cc[i], specs[i], ra.d[i]));
+    }
+    INB_CUDA(cudaEventRecord(e1, L->wst[1]));
+    INB_CUDA(cudaEventRecord(e2, L->wst[2]));
+    INB_CUDA(cudaStreamWaitEvent(L->wst[0], e1, 0));
+    INB_CUDA(cudaStreamWaitEvent(L->wst[0], e2, 0));
+    {
+      Prof pf(cc[0], F_WGRAD_TC, 1, 0, 0);
+      dim3 grid((unsigned)std::min<long long>(cdiv(outs, 64), 148 * 4), (unsigned)n, 1);
+      k_wgrad_reduce<<<grid, 256, 0, L->wst[0]>>>(ra);
+      INB_CUDA(cudaGetLastError());
+    }
+    INB_CUDA(cudaEventRecord(ed, L->wst[0]));
+    L->wdone[L->wparity] = ed;
+    L->wpending[L->wparity] = true;
+    c.ar->release(mk);  // the partial tiles stay untouched: nothing else is allocated in this step's region afterwards
+    return;
+  }
   if (side_by_side) {
     cudaEvent_t ef = L->wev[L->wnext], e1 = L->wev[L->wnext + 1], e2 = L->wev[L->wnext + 2];
     L->wnext += 3;
