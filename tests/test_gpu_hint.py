@@ -207,3 +207,23 @@ def test_multiscale_hint_cfg4_full_size_properties():
     assert abs(lhs - rhs) < 1e-2 * rhs, (lhs, rhs)
     # and it is linear in dZ beyond the constant: dX(2 dZ) - dX(dZ) = dX(dZ) - dX(0)
     assert rel(net.backward(2 * dZr, Z)[0] - dX1, dX1 - dX0) < 1e-4
+
+
+def test_cuda_hint_matches_golden():
+    """The CUDA path against the committed oracle vectors (tests/golden/hint_small.npz)."""
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hint_small.npz"))
+    n_in, nh, Ls, K = [int(v) for v in gold["hint_cfg"]]
+    net = inb200.NetworkMultiScaleHINT(n_in, nh, Ls, K, split_scales=True, k2=1, p2=0, device=DEV)
+    nparam = sum(1 for k in gold.files if k.startswith("hint_p"))
+    inb200.set_params(net, [torch.from_numpy(gold[f"hint_p{i:03d}"]) for i in range(nparam)])
+    X = torch.from_numpy(gold["hint_X"])
+    Z, ld = net.forward(g(X))
+    assert rel(Z, torch.from_numpy(gold["hint_Z"])) < TOL_OUT
+    assert abs(ld.item() - float(gold["hint_logdet"])) < TOL_LOGDET * abs(float(gold["hint_logdet"])) + 1e-4
+    dX, Xr = net.backward(Z / X.shape[0], Z)
+    assert rel(Xr, X) < 1e-3
+    assert rel(dX, torch.from_numpy(gold["hint_dX"])) < 10 * TOL_OUT
+    for i, p in enumerate(net.get_params()):
+        assert rel(p.grad, torch.from_numpy(gold[f"hint_g{i:03d}"])) < 10 * TOL_GRAD, i

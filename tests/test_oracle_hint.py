@@ -170,3 +170,25 @@ def test_hint_plan_errors():
         mk(n_in=3)       # 12 channels: Int(12/8) is inexact (hint.jl:86)
     with pytest.raises(L.InbError, match="padding"):
         mk(p2=0)
+
+
+def test_hint_oracle_matches_golden():
+    """tests/golden/hint_small.npz (make_golden.py: float64 oracle on seeded inputs) pins the HINT oracle against drift;
+    oracle-generated, not reference-generated ('parity unpinned', oracle/hint_oracle.py)."""
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hint_small.npz"))
+    n_in, nh, Ls, K = [int(v) for v in gold["hint_cfg"]]
+    N = H.NetworkMultiScaleHINT(n_in, nh, Ls, K, split_scales=True, k2=1, p2=0, seed=7, dtype=DT)
+    ps = N.get_params()
+    for i, p in enumerate(ps):
+        p.data = torch.from_numpy(gold[f"hint_p{i:03d}"]).double()
+    X = torch.from_numpy(gold["hint_X"]).double()
+    Z, ld = N.forward(X)
+    dX, Xr = N.backward(Z / X.shape[0], Z)
+    assert rel(Z, torch.from_numpy(gold["hint_Z"])) < 1e-12
+    assert abs(float(ld) - float(gold["hint_logdet"])) < 1e-10 * abs(float(gold["hint_logdet"]))
+    assert rel(dX, torch.from_numpy(gold["hint_dX"])) < 1e-10
+    assert rel(Xr, X) < 1e-4
+    for i, p in enumerate(ps):
+        assert rel(p.grad, torch.from_numpy(gold[f"hint_g{i:03d}"])) < 1e-10, i
