@@ -155,7 +155,7 @@ def run_reference(args, cfg, cfg_name):
                          "note": "torch-CPU oracle restatement of the Julia reference (no Julia in the image)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(cfg, name, global_batch, precision):
@@ -165,7 +165,30 @@ def workload_config(cfg, name, global_batch, precision):
             "l2": "activations per step >> 126 MB L2 (no flush needed)" if name == "cfg2" else "L2-resident (latency bound)"}
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 at
+    communicator creation), so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -393,7 +416,7 @@ def main():
                                 "sample": f"{nst} steps of batch {sb} of the full {args.config} network on the host "
                                           f"cores (torch-CPU oracle restating the Julia reference, {threads} threads, "
                                           f"{sec * nst:.1f} s)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
