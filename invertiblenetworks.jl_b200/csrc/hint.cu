@@ -90,6 +90,21 @@ static void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa
   c.ar->release(m);
 }
 
+// A CL[j] is applied 2^(j-1) times per pass with the same weights: its chain operands are packed once per pass
+// (direction 0: forward / recompute, 1: backward) instead of once per visit.  Returns a copy of `p` whose RBParams
+// point at the packed planes (allocated in the caller's arena scope, `store` keeps the descriptors alive).
+static HintParams hint_prepack(Ctx& c, const HintShape& h, const HintParams& p, bool backward, std::vector<PackedW>& store) {
+  HintParams q = p;
+  const int n = (int)p.cl.size();
+  store.resize(2 * n);
+  for (int j = 0; j < n; ++j) {
+    const RBShape rs = basic_rb(h, h.C >> (j + 1));
+    if (rb_prepack_chain(c, rs, &p.cl[j], 1, 0, &store[2 * j])) q.cl[j].pre[0] = &store[2 * j];
+    if (backward && rb_prepack_chain(c, rs, &p.cl[j], 1, 1, &store[2 * j + 1])) q.cl[j].pre[1] = &store[2 * j + 1];
+  }
+  return q;
+}
+
 static void rec_forward(Ctx& c, const HintShape& h, View x, int C, int scale, const HintParams& p, double* ld) {
   const int Ca = C / 2;
   View xa = x, xb = sub(x, Ca, h.g.px);
@@ -145,13 +160,23 @@ void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& 
     View yb = sub(y, Ca, px);
     op_an_hh_fwd(c, px, h.B, h.C - Ca, yb, yb, nullptr, nullptr, p.v1, p.v2, p.v3, nullptr);
   }
-  rec_forward(c, h, y, h.C, 1, p, ld);
+  size_t m = c.ar->mark();
+  std::vector<PackedW> store;
+  const HintParams q = hint_prepack(c, h, p, false, store);
+  rec_forward(c, h, y, h.C, 1, q, ld);
+  c.ar->release(m);
 }
 
 void hint_inverse(Ctx& c, const HintShape& h, View y, View x, const HintParams& p) {
   const long long px = h.g.px;
   const bool full = h.permute == HINT_PERMUTE_FULL;
-  rec_inverse(c, h, y, h.C, 1, p);
+  {
+    size_t m = c.ar->mark();
+    std::vector<PackedW> store;
+    const HintParams q = hint_prepack(c, h, p, false, store);
+    rec_inverse(c, h, y, h.C, 1, q);
+    c.ar->release(m);
+  }
   if (h.permute == HINT_PERMUTE_LOWER) {  // :193
     const int Ca = h.C / 2;
     View yb = sub(y, Ca, px);
@@ -169,7 +194,9 @@ void hint_backward(Ctx& c, const HintShape& h, View dy, View y, View dx, View x,
   const bool full = h.permute == HINT_PERMUTE_FULL, lower = h.permute == HINT_PERMUTE_LOWER;
   size_t m = c.ar->mark();
   std::vector<char> seen(p.cl.size(), 0);
-  rec_backward(c, h, dy, y, h.C, 1, p, g, seen);
+  std::vector<PackedW> store;
+  const HintParams q = hint_prepack(c, h, p, true, store);
+  rec_backward(c, h, dy, y, h.C, 1, q, g, seen);
   const int Cm = lower ? h.C - h.C / 2 : h.C;  // channels the Householder mix acts on
   double* gram = c.ar->f64((size_t)Cm * Cm + 2 * h.C);
   double* dsdb = gram + (size_t)Cm * Cm;
