@@ -14,6 +14,7 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace inb {
@@ -284,6 +285,90 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
     __syncwarp();
   }
 }
+// The same rows for the shapes the chain sees most (2-D, 3x3, one source tensor, C channels known at compile time): the
+// column -> (tap, channel) map, the nine neighbour offsets and the nine border predicates live in registers, so an
+// element costs an address add and a predicated load instead of two shared-memory lookups, a bit test and two selects
+// (the generic kernel is issue-bound at half of the HBM rate).  Output bit-identical to k_im2col_tc.
+template <int C>
+__global__ void __launch_bounds__(kI2cThreads)
+k_im2col9_tc(const float* __restrict__ in0, long long in0_bs, int W, int H, long long px, long long M, int ones_col,
+             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  constexpr int KR = 9 * C, KP = (KR + 63) / 64 * 64;
+  __shared__ __align__(16) unsigned char s_tile[kI2cThreads / 32][2][32 * kI2cRow];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long m0 = (long long)blockIdx.x * kI2cPix + wid * 32;  // first pixel of this warp
+  if (m0 >= M) return;
+  const long long m = m0 + lane;
+  const bool live = m < M;
+  const long long mc = live ? m : M - 1;
+  const long long b = mc / px;
+  const int pix = (int)(mc - b * px);
+  const int y = pix / W, x = pix - y * W;
+  bool ok[9];
+  int doff[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+    ok[tap] = live && x + dx >= 0 && x + dx < W && y + dy >= 0 && y + dy < H;
+    doff[tap] = dy * W + dx;
+  }
+  const float* p0 = in0 + b * in0_bs + pix;
+  const int ipx = (int)px;
+  unsigned char* th = s_tile[wid][0];
+  unsigned char* tl = s_tile[wid][1];
+#pragma unroll
+  for (int kb = 0; kb < KP; kb += 64) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = kb + g * 16 + j;  // compile-time after unrolling
+        if (k < KR) {
+          const int tap = k / C, ch = k - tap * C;
+          v[j] = ok[tap] ? __ldg(p0 + (ch * ipx + doff[tap])) : 0.f;
+        } else {
+          v[j] = (k == ones_col) ? 1.f : 0.f;
+        }
+      }
+      uint32_t wh[8], wl[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float a = v[2 * q], bb = v[2 * q + 1];
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
+        wh[q] = hw;
+        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
+      }
+      const int o = lane * kI2cRow + g * 32;
+      *reinterpret_cast<uint4*>(th + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      *reinterpret_cast<uint4*>(th + o + 16) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+      *reinterpret_cast<uint4*>(tl + o) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      *reinterpret_cast<uint4*>(tl + o + 16) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int id = it * 32 + lane, row = id >> 3, ch = id & 7;
+      if (m0 + row < M) {
+        const long long o = (m0 + row) * KP + kb + ch * 8;
+        *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(th + row * kI2cRow + ch * 16);
+        *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(tl + row * kI2cRow + ch * 16);
+      }
+    }
+    __syncwarp();
+  }
+}
+template <int C>
+static void launch_im2col9(Ctx& c, const Geo& g, long long M, const float* in0, long long in0_bs, int ones_col, Planes out) {
+  k_im2col9_tc<C><<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, g.W, g.H, g.px, M, ones_col, out.hi, out.lo);
+}
+static bool im2col_fast_enabled() {
+  static const bool on = [] { const char* e = getenv("INB_IM2COL_FAST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
                   long long in1_bs, int C, int kp, int ones_col, Planes out) {
   if (c.dry()) return;
@@ -292,6 +377,25 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   INB_CHECK(kp <= kI2cMaxK && kp % 64 == 0, "im2col: unsupported row width %d", kp);
   INB_CHECK((long long)C * g.px + 2 * g.px < (1ll << 31), "im2col: sample too large for 32-bit offsets");
   Prof pf(c, F_LAYOUT_TC, 1, 0, (4.0 * C + 4.0 * kp) * M);
+  if (k == 3 && g.nd == 2 && (in1 == nullptr || c0 >= C) && kp == (9 * C + 63) / 64 * 64 && im2col_fast_enabled()) {
+    bool done = true;
+    switch (C) {
+      case 2: launch_im2col9<2>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 4: launch_im2col9<4>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 6: launch_im2col9<6>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 8: launch_im2col9<8>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 12: launch_im2col9<12>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 16: launch_im2col9<16>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 24: launch_im2col9<24>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 32: launch_im2col9<32>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 48: launch_im2col9<48>(c, g, M, in0, in0_bs, ones_col, out); break;
+      default: done = false;
+    }
+    if (done) {
+      INB_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   k_im2col_tc<<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
                                                           kp, ones_col, out.hi, out.lo);
   INB_CUDA(cudaGetLastError());
