@@ -1557,7 +1557,7 @@ __global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
 // are adjacent lanes, so a warp instruction touches ~11 pixels x G chunks = a third of the cache lines the
 // thread-per-pixel walk does (that one is L1-transaction bound: 32 lines per instruction).  Needs 16-byte aligned
 // groups: cstride and the pitch multiples of 4 (always true for the tap-row sums Pq).
-template <int G>
+template <int G, bool Q2 = false>
 __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
   // grid (pixels of a sample / 32, sample): the pixel decode is 32-bit (the kernel is instruction-bound; the 64-bit
   // divisions of a flat pixel index were most of its instructions)
@@ -1571,6 +1571,18 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
   const int y = yz % a.H;
   const int z = yz / a.H;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (Q2) {
+    // 2-D tap-row sums (three rows dy = -1, 0, 1): the three loads are issued together (the rolled loop below keeps one
+    // load in flight per thread and the kernel is latency-bound)
+    const float* row = a.P + m * a.n3pad + 4 * g;
+    const long long rs = (long long)a.W * a.n3pad;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 w0 = (y > 0) ? __ldg(reinterpret_cast<const float4*>(row - rs)) : zero;
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(row + a.cstride));
+    const float4 w2 = (y + 1 < a.H) ? __ldg(reinterpret_cast<const float4*>(row + rs + 2 * a.cstride)) : zero;
+    acc.x = (w0.x + w1.x) + w2.x; acc.y = (w0.y + w1.y) + w2.y;
+    acc.z = (w0.z + w1.z) + w2.z; acc.w = (w0.w + w1.w) + w2.w;
+  } else
   for (int tap = 0; tap < a.taps; ++tap) {
     int dx, dy, dz;
     if (a.qsum) { dx = 0; dy = tap % 3 - 1; dz = (a.D > 1) ? tap / 3 - 1 : 0; }
@@ -1885,7 +1897,13 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     const dim3 nbg((unsigned)cdiv(s.g.px, 32), (unsigned)s.B, 1);
 
     static const bool no_g = [] { const char* e = getenv("INB_COL2IM_G"); return e && e[0] == '0'; }();
-    if (g4 && !no_g && G == 2) k_col2im_g<2><<<nbg, 64, 0, c.st>>>(ca);
+    static const bool no_q2 = [] { const char* e = getenv("INB_COL2IM_Q2"); return e && e[0] == '0'; }();
+    const bool q2 = g4 && !no_g && !no_q2 && a.qsum && s.g.D == 1 && ca.taps == 3;
+    if (q2 && G == 2) k_col2im_g<2, true><<<nbg, 64, 0, c.st>>>(ca);
+    else if (q2 && G == 3) k_col2im_g<3, true><<<nbg, 96, 0, c.st>>>(ca);
+    else if (q2 && G == 6) k_col2im_g<6, true><<<nbg, 192, 0, c.st>>>(ca);
+    else if (q2 && G == 12) k_col2im_g<12, true><<<nbg, 384, 0, c.st>>>(ca);
+    else if (g4 && !no_g && G == 2) k_col2im_g<2><<<nbg, 64, 0, c.st>>>(ca);
     else if (g4 && !no_g && G == 3) k_col2im_g<3><<<nbg, 96, 0, c.st>>>(ca);
     else if (g4 && !no_g && G == 6) k_col2im_g<6><<<nbg, 192, 0, c.st>>>(ca);
     else if (g4 && !no_g && G == 12) k_col2im_g<12><<<nbg, 384, 0, c.st>>>(ca);
