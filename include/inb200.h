@@ -175,6 +175,20 @@ int inb_haar_unsqueeze(int nx, int ny, int B, int C, int type, const float* Y, f
  * shared_grads: a CL[j], j > 1, is applied 2^(j-1) times per pass; 0 = its gradient is the sum over the visits (the true
  * gradient; the reference's set_grad=false path, :222), 1 = only the last visit survives (what the reference's
  * set_grad=true path leaves in .grad, layer_residual_block.jl:168-172). */
+/* CouplingLayerBasic (invertible_layer_basic.jl:62-149): X1 conditions, X2 is transformed, both (B, C1, spatial);
+ * rbparams = RB.(W1 (k1..,C1,nh), W2, W3 (k1..,2*C1,nh), b1, b2).  forward: Y2 = S.*X2 + T (Y1 = X1 is the caller's);
+ * inverse: X2; backward: dX1 = RB.backward(...) + dY1, dX2, X2 recomputed, the five gradients written. */
+int inb_basic_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                               float high, int precision, const float* X1, const float* X2, float* const* rbparams,
+                               float* Y2, float* logdet /* nullable */, void* stream);
+int inb_basic_coupling_inverse(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                               float high, int precision, const float* Y1, const float* Y2, float* const* rbparams,
+                               float* X2, void* stream);
+int inb_basic_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                                float high, int logdet, int precision, const float* dY1, const float* dY2,
+                                const float* Y1, const float* Y2, float* const* rbparams, float* const* rbgrads,
+                                float* dX1, float* dX2, float* X2, void* stream);
+
 #define INB_PERMUTE_NONE 0
 #define INB_PERMUTE_FULL 1
 #define INB_PERMUTE_LOWER 2

@@ -12,7 +12,7 @@ from .glow import (ADAM, ActNorm, Conv1x1, CouplingLayerGlow, NetworkConditional
                    Parameter, ResidualBlock, clear_grad, get_grads, get_params, nll_grad, set_params, squeeze,
                    unsqueeze)
 
-from .hint import (CouplingLayerHINT, Haar_squeeze, NetworkMultiScaleHINT, get_depth, invHaar_unsqueeze,
+from .hint import (CouplingLayerBasic, CouplingLayerHINT, Haar_squeeze, NetworkMultiScaleHINT, get_depth, invHaar_unsqueeze,
                    wavelet_squeeze, wavelet_unsqueeze)
 
 ConditionalLayerGlow = CouplingLayerGlow  # same class with n_cond > 0 (conditional_layer_glow.jl:61-66)
@@ -20,6 +20,6 @@ ConditionalLayerGlow = CouplingLayerGlow  # same class with n_cond > 0 (conditio
 __all__ = [
     "ADAM", "ActNorm", "Conv1x1", "CouplingLayerGlow", "ConditionalLayerGlow", "NetworkConditionalGlow", "NetworkGlow",
     "NetworkGlow3D", "Parameter", "ResidualBlock", "clear_grad", "get_grads", "get_params", "nll_grad",
-    "set_params", "squeeze", "unsqueeze", "CouplingLayerHINT", "NetworkMultiScaleHINT", "Haar_squeeze",
+    "set_params", "squeeze", "unsqueeze", "CouplingLayerBasic", "CouplingLayerHINT", "NetworkMultiScaleHINT", "Haar_squeeze",
     "invHaar_unsqueeze", "wavelet_squeeze", "wavelet_unsqueeze", "get_depth", "InbError", "PRECISIONS", "lib", "dp",
 ]

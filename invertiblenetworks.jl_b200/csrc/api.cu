@@ -1115,6 +1115,67 @@ static HintGrads hint_grads(const HintShape& h, float* const* t) {
   return g;
 }
 
+static HintShape basic_shape(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                             float high, int logdet) {
+  INB_CHECK(ndims == 2 || ndims == 3, "ndims must be 2 or 3");
+  INB_CHECK(B > 0 && nh > 0 && C1 > 0, "bad shape");
+  INB_CHECK((k1 == 1 || k1 == 3) && (k2 == 1 || k2 == 3), "supported kernel sizes are 1 and 3");
+  INB_CHECK(high > low, "sigmoid high must exceed low");
+  HintShape h{};
+  h.g = make_geo(ndims, nx, ny, nz);
+  h.B = B; h.C = 2 * C1; h.nh = nh; h.k1 = k1; h.k2 = k2; h.low = low; h.high = high; h.logdet = logdet;
+  return h;
+}
+int inb_basic_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                               float high, int precision, const float* X1, const float* X2, float* const* rbparams,
+                               float* Y2, float* logdet, void* stream) {
+  return guarded([&] {
+    INB_CHECK(X1 && X2 && Y2 && rbparams, "null argument");
+    HintShape h = basic_shape(ndims, nx, ny, nz, B, C1, nh, k1, k2, low, high, logdet != nullptr);
+    RBParams p{rbparams[0], rbparams[1], rbparams[2], rbparams[3], rbparams[4]};
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      const long long bs = C1 * h.g.px;
+      double* ld = logdet ? c.ar->f64(1) : nullptr;
+      if (ld) op_zero(c, ld, sizeof(double));
+      op_copy(c, h.g.px, B, C1, view(const_cast<float*>(X2), bs), view(Y2, bs));
+      basic_forward(c, h, C1, view(const_cast<float*>(X1), bs), view(Y2, bs), p, ld);
+      if (ld) op_ld_finish(c, ld, logdet);
+    });
+  });
+}
+int inb_basic_coupling_inverse(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                               float high, int precision, const float* Y1, const float* Y2, float* const* rbparams,
+                               float* X2, void* stream) {
+  return guarded([&] {
+    INB_CHECK(Y1 && Y2 && X2 && rbparams, "null argument");
+    HintShape h = basic_shape(ndims, nx, ny, nz, B, C1, nh, k1, k2, low, high, 0);
+    RBParams p{rbparams[0], rbparams[1], rbparams[2], rbparams[3], rbparams[4]};
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      const long long bs = C1 * h.g.px;
+      op_copy(c, h.g.px, B, C1, view(const_cast<float*>(Y2), bs), view(X2, bs));
+      basic_inverse(c, h, C1, view(const_cast<float*>(Y1), bs), view(X2, bs), p);
+    });
+  });
+}
+int inb_basic_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C1, int nh, int k1, int k2, float low,
+                                float high, int logdet, int precision, const float* dY1, const float* dY2,
+                                const float* Y1, const float* Y2, float* const* rbparams, float* const* rbgrads,
+                                float* dX1, float* dX2, float* X2, void* stream) {
+  return guarded([&] {
+    INB_CHECK(dY1 && dY2 && Y1 && Y2 && rbparams && rbgrads && dX1 && dX2 && X2, "null argument");
+    HintShape h = basic_shape(ndims, nx, ny, nz, B, C1, nh, k1, k2, low, high, logdet);
+    RBParams p{rbparams[0], rbparams[1], rbparams[2], rbparams[3], rbparams[4]};
+    RBGrads g{rbgrads[0], rbgrads[1], rbgrads[2], rbgrads[3], rbgrads[4]};
+    with_temp_arena((cudaStream_t)stream, precision, [&](Ctx& c) {
+      const long long bs = C1 * h.g.px;
+      op_copy(c, h.g.px, B, C1, view(const_cast<float*>(Y2), bs), view(X2, bs));
+      op_copy(c, h.g.px, B, C1, view(const_cast<float*>(dY2), bs), view(dX2, bs));
+      op_copy(c, h.g.px, B, C1, view(const_cast<float*>(dY1), bs), view(dX1, bs));  // + dY1 of basic.jl:137
+      basic_backward(c, h, C1, view(const_cast<float*>(Y1), bs), view(dX1, bs), view(X2, bs), view(dX2, bs), p, g, false);
+    });
+  });
+}
+
 int inb_hint_depth(int C) {
   HintShape h{};
   h.C = C;

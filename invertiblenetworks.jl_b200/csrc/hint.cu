@@ -35,7 +35,7 @@ static RBShape basic_rb(const HintShape& h, int Ca) {
 }
 
 // CL.forward(X1 = xa, X2 = xb): xb <- S .* xb + T                        basic.jl:96-98
-static void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld) {
+void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld) {
   const RBShape rs = basic_rb(h, Ca);
   size_t m = c.ar->mark();
   RBHidden hid;
@@ -48,7 +48,7 @@ static void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, 
   c.ar->release(m);
 }
 // CL.inverse(Y1 = xa, Y2 = yb): yb <- (yb - T) ./ (S + eps)               basic.jl:112-114
-static void basic_inverse(Ctx& c, const HintShape& h, int Ca, View xa, View yb, const RBParams& p) {
+void basic_inverse(Ctx& c, const HintShape& h, int Ca, View xa, View yb, const RBParams& p) {
   const RBShape rs = basic_rb(h, Ca);
   size_t m = c.ar->mark();
   RBHidden hid;
@@ -62,7 +62,7 @@ static void basic_inverse(Ctx& c, const HintShape& h, int Ca, View xa, View yb, 
 }
 // CL.backward(dY1 = 0, dY2 = dyb, Y1 = xa, Y2 = yb) with its dX1 ADDED to dxa (hint.jl:231,248 / :253,264):
 // (dyb, yb) <- (dX2, X2) in place                                          basic.jl:127-137
-static void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa, View yb, View dyb,
+void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa, View yb, View dyb,
                            const RBParams& p, const RBGrads& g, bool accumulate) {
   const RBShape rs = basic_rb(h, Ca);
   size_t m = c.ar->mark();

@@ -69,6 +69,61 @@ def _hint_shapes(n_in, n_hidden, k1, k2, ndims, with_conv):
     return shapes
 
 
+class CouplingLayerBasic:
+    """L = CouplingLayerBasic(n_in, n_hidden; k1, k2, p1, p2, logdet, activation=SigmoidLayer(low, high))
+    invertible_layer_basic.jl:79-86: X1 (n_in channels) conditions, X2 (n_in channels) is transformed."""
+
+    def __init__(self, n_in: int, n_hidden: int, *, k1=3, k2=3, p1=1, p2=1, logdet=False, ndims=2, low=0.0, high=1.0,
+                 precision="fp32", gen: Optional[torch.Generator] = None, device="cuda"):
+        if p1 != (k1 - 1) // 2 or p2 != (k2 - 1) // 2:
+            raise _l.InbError("only 'same' padding is supported on the B200 path")
+        gen = gen or torch.Generator().manual_seed(0)
+        self.n_in, self.n_hidden, self.k1, self.k2, self.ndims = n_in, n_hidden, k1, k2, ndims
+        self.logdet, self.low, self.high, self.precision = logdet, low, high, _l.PRECISIONS[precision]
+        shapes = [(n_hidden, n_in) + (k1,) * ndims, (n_hidden, n_hidden) + (k2,) * ndims,
+                  (n_hidden, 2 * n_in) + (k1,) * ndims, (n_hidden,), (n_hidden,)]
+        self._params = [Parameter(_glorot(gen, *s, device=device) if len(s) > 1 else torch.zeros(s, device=device))
+                        for s in shapes]
+
+    def get_params(self) -> List[Parameter]:
+        return self._params
+
+    def _args(self, X1, X2):
+        nd, nx, ny, nz = _geom(X1)
+        if X1.shape != X2.shape or X1.shape[1] != self.n_in:
+            raise _l.InbError(f"expected two tensors of {self.n_in} channels and equal shape")
+        return [nd, nx, ny, nz, X1.shape[0], self.n_in, self.n_hidden, self.k1, self.k2, self.low, self.high]
+
+    def forward(self, X1: Tensor, X2: Tensor):
+        """X1, Y2[, logdet] = L.forward(X1, X2)   (:90-105)"""
+        X1, X2 = _check(X1, "X1"), _check(X2, "X2")
+        Y2 = torch.empty_like(X2)
+        ld = torch.empty(1, device=X1.device) if self.logdet else None
+        _l.call("inb_basic_coupling_forward", *self._args(X1, X2), self.precision, _l.ptr(X1), _l.ptr(X2),
+                _l.ptr_table([p.data for p in self._params]), _l.ptr(Y2), _l.ptr(ld), _l.stream())
+        return (X1, Y2, ld[0]) if self.logdet else (X1, Y2)
+
+    def inverse(self, Y1: Tensor, Y2: Tensor):
+        """Y1, X2 = L.inverse(Y1, Y2)   (:108-121)"""
+        Y1, Y2 = _check(Y1, "Y1"), _check(Y2, "Y2")
+        X2 = torch.empty_like(Y2)
+        _l.call("inb_basic_coupling_inverse", *self._args(Y1, Y2), self.precision, _l.ptr(Y1), _l.ptr(Y2),
+                _l.ptr_table([p.data for p in self._params]), _l.ptr(X2), _l.stream())
+        return Y1, X2
+
+    def backward(self, dY1: Tensor, dY2: Tensor, Y1: Tensor, Y2: Tensor):
+        """dX1, dX2, X1, X2 = L.backward(dY1, dY2, Y1, Y2)   (:124-149, set_grad=true)"""
+        dY1, dY2, Y1, Y2 = _check(dY1, "dY1"), _check(dY2, "dY2"), _check(Y1, "Y1"), _check(Y2, "Y2")
+        dX1, dX2, X2 = torch.empty_like(Y1), torch.empty_like(Y2), torch.empty_like(Y2)
+        g = [torch.empty_like(p.data) for p in self._params]
+        _l.call("inb_basic_coupling_backward", *self._args(Y1, Y2), int(self.logdet), self.precision, _l.ptr(dY1),
+                _l.ptr(dY2), _l.ptr(Y1), _l.ptr(Y2), _l.ptr_table([p.data for p in self._params]), _l.ptr_table(g),
+                _l.ptr(dX1), _l.ptr(dX2), _l.ptr(X2), _l.stream())
+        for p, t in zip(self._params, g):  # layer_residual_block.jl:168-172: overwritten
+            p.grad = t
+        return dX1, dX2, Y1, X2
+
+
 class CouplingLayerHINT:
     """H = CouplingLayerHINT(n_in, n_hidden; logdet, permute, k1, k2, p1, p2, activation=SigmoidLayer(low, high))
     invertible_layer_hint.jl:78-101.  permute in {"none", "full", "lower"}."""

@@ -78,6 +78,9 @@ SIGNATURES = {
     "inb_unsqueeze": (I, [I, I, I, I, I, I, P, P, P]),
     "inb_haar_squeeze": (I, [I, I, I, I, I, P, P, P]),
     "inb_haar_unsqueeze": (I, [I, I, I, I, I, P, P, P]),
+    "inb_basic_coupling_forward": (I, [I] * 9 + [F, F, I, P, P, PP, P, P, P]),
+    "inb_basic_coupling_inverse": (I, [I] * 9 + [F, F, I, P, P, PP, P, P]),
+    "inb_basic_coupling_backward": (I, [I] * 9 + [F, F, I, I, P, P, P, P, PP, PP, P, P, P, P]),
     "inb_hint_depth": (I, [I]),
     "inb_hint_coupling_forward": (I, [I] * 9 + [F, F, I, I, P, PP, P, P, P]),
     "inb_hint_coupling_inverse": (I, [I] * 9 + [F, F, I, I, P, PP, P, P]),

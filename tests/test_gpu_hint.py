@@ -227,3 +227,33 @@ def test_cuda_hint_matches_golden():
     assert rel(dX, torch.from_numpy(gold["hint_dX"])) < 10 * TOL_OUT
     for i, p in enumerate(net.get_params()):
         assert rel(p.grad, torch.from_numpy(gold[f"hint_g{i:03d}"])) < 10 * TOL_GRAD, i
+
+
+@pytest.mark.parametrize("C1,k2,logdet", [(2, 3, True), (4, 1, True), (6, 3, False)])
+def test_basic_coupling_parity(C1, k2, logdet):
+    """CouplingLayerBasic (invertible_layer_basic.jl:90-149) against the oracle; invertibility of
+    test_coupling_layer_basic.jl (forward -> inverse, forward -> backward recompute)."""
+    torch.manual_seed(C1)
+    nh, p2 = 8, (k2 - 1) // 2
+    gen = torch.Generator().manual_seed(9)
+    ws = [O.glorot_uniform(gen, nh, C1, 3, 3), O.glorot_uniform(gen, nh, nh, k2, k2), O.glorot_uniform(gen, nh, 2 * C1, 3, 3),
+          0.1 * torch.randn(nh), 0.1 * torch.randn(nh)]
+    L64 = H.CouplingLayerBasic(O.ResidualBlock(*[w.double() for w in ws], p1=1, p2=p2), logdet=logdet)
+    L = inb200.CouplingLayerBasic(C1, nh, k2=k2, p2=p2, logdet=logdet, device=DEV)
+    inb200.set_params(L, ws)
+    X1, X2 = torch.randn(3, C1, 12, 10), torch.randn(3, C1, 12, 10)
+    _, Y2_64, ld64 = L64.forward(X1.double(), X2.double())
+    out = L.forward(g(X1), g(X2))
+    assert rel(out[1], Y2_64) < TOL_OUT
+    if logdet:
+        assert abs(out[2].item() - ld64.item()) < TOL_LOGDET * abs(ld64.item()) + 1e-6
+    assert rel(L.inverse(g(X1), out[1])[1], X2) < 1e-5
+    Y2 = Y2_64.float()
+    dY1, dY2 = torch.randn_like(X1), torch.randn_like(X2)
+    dX1, dX2, _, X2r = L.backward(g(dY1), g(dY2), g(X1), g(Y2))
+    with FragileUnits(1e-6) as fr:
+        dX1_64, dX2_64, _, X2_64 = L64.backward(dY1.double(), dY2.double(), X1.double(), Y2.double())
+    assert rel(X2r, X2_64) < TOL_OUT and rel(dX2, dX2_64) < TOL_OUT
+    assert_grad_close(dX1, dX1_64, TOL_OUT, fr, "dX1")
+    for i, (p, q) in enumerate(zip(L.get_params(), L64.params())):
+        assert_grad_close(p.grad, q.grad, TOL_GRAD, fr, f"gradient {i}")
