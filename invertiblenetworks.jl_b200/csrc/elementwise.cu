@@ -962,12 +962,12 @@ static int pick_vec_ew(long long px, std::initializer_list<const View*> vs, cons
 }
 
 void op_coupling_fwd(Ctx& c, long long px, int B, int C1, View x1, View y1, const float* rb, float low,
-                     float high, double* ld) {
+                     float high, double* ld, int ld_batch) {
   if (c.dry()) return;
   Prof pf(c, F_COUPLING_FWD, 1, 0, 16.0 * B * C1 * px);
   int V = pick_vec_ew(px, {&x1, &y1}, rb);
   const dim3 grid = coupling_grid(px / V, C1, B);
-  float invB = 1.f / (float)B;
+  float invB = 1.f / (float)(ld_batch > 0 ? ld_batch : B);
   if (V == 4) k_coupling_fwd<4><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);
   else if (V == 2) k_coupling_fwd<2><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);
   else k_coupling_fwd<1><<<grid, 256, 0, c.st>>>(x1.p, x1.bs, y1.p, y1.bs, rb, px, C1, low, high, ld, invB);

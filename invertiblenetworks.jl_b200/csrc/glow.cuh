@@ -109,7 +109,7 @@ void hint_check(const HintShape& h);
 // CouplingLayerBasic on views (h.C is ignored, Ca = channels of X1 = channels of X2; invertible_layer_basic.jl:90-149):
 //   forward  xb <- S .* xb + T with (logS, T) = RB(xa)           inverse  yb <- (yb - T) ./ (S + eps)
 //   backward (dyb, yb) <- (dX2, X2) in place, dxa += RB.backward(...) (the caller pre-loads dxa with dY1)
-void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld);
+void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld, int ld_batch = 0);
 void basic_inverse(Ctx& c, const HintShape& h, int Ca, View xa, View yb, const RBParams& p);
 void basic_backward(Ctx& c, const HintShape& h, int Ca, View xa, View dxa, View yb, View dyb, const RBParams& p,
                     const RBGrads& g, bool accumulate);

@@ -35,7 +35,7 @@ static RBShape basic_rb(const HintShape& h, int Ca) {
 }
 
 // CL.forward(X1 = xa, X2 = xb): xb <- S .* xb + T                        basic.jl:96-98
-void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld) {
+void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const RBParams& p, double* ld, int ld_batch) {
   const RBShape rs = basic_rb(h, Ca);
   size_t m = c.ar->mark();
   RBHidden hid;
@@ -44,7 +44,7 @@ void basic_forward(Ctx& c, const HintShape& h, int Ca, View xa, View xb, const R
   hid.G = nullptr;
   float* Y3 = c.ar->f32((size_t)h.B * rs.Cout * h.g.px);
   rb_forward(c, rs, xa, view(nullptr, 0), p, hid, Y3);
-  op_coupling_fwd(c, h.g.px, h.B, Ca, xb, xb, Y3, h.low, h.high, h.logdet ? ld : nullptr);
+  op_coupling_fwd(c, h.g.px, h.B, Ca, xb, xb, Y3, h.low, h.high, h.logdet ? ld : nullptr, ld_batch);
   c.ar->release(m);
 }
 // CL.inverse(Y1 = xa, Y2 = yb): yb <- (yb - T) ./ (S + eps)               basic.jl:112-114
@@ -163,7 +163,26 @@ void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& 
   size_t m = c.ar->mark();
   std::vector<PackedW> store;
   const HintParams q = hint_prepack(c, h, p, false, store);
-  rec_forward(c, h, y, h.C, 1, q, ld);
+  static const bool no_levels = [] { const char* e = getenv("INB_HINT_LEVELS"); return e && e[0] == '0'; }();
+  const int n = h.depth();
+  if (n > 1 && !no_levels && y.bs == (long long)h.C * px && (long long)h.B * (1 << (n - 1)) <= 65535) {
+    // Level-synchronous forward.  In the forward direction every coupling conditions on the UNTRANSFORMED first half
+    // of its group (hint.jl:131-133 pass the input slices down), so all 2^(s-1) groups of level s are independent
+    // given the levels below, and they share CL[s].  The groups tile the channel axis, hence (sample, group) is one
+    // uniform batch stride of 2*Ca*px elements: a level is ONE coupling call on B * 2^(s-1) virtual samples, reading
+    // the conditioning halves from a pristine copy and transforming the second halves of the working tensor in place
+    // (n calls instead of 2^n - 1).  The inverse and backward directions are inherently depth-first (rec_*).
+    float* y0 = c.ar->f32((size_t)h.B * h.C * px);
+    op_copy(c, px, h.B, h.C, y, view(y0, (long long)h.C * px));
+    for (int s = n; s >= 1; --s) {
+      const int Ca = h.C >> s, G = 1 << (s - 1);
+      HintShape hv = h;
+      hv.B = h.B * G;
+      basic_forward(c, hv, Ca, view(y0, 2LL * Ca * px), view(y.p + (long long)Ca * px, 2LL * Ca * px), q.cl[s - 1], ld, h.B);
+    }
+  } else {
+    rec_forward(c, h, y, h.C, 1, q, ld);
+  }
   c.ar->release(m);
 }
 

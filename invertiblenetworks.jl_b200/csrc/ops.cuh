@@ -41,8 +41,9 @@ void op_an_grad_finish(Ctx& c, int C, long long px, const double* dsdb, const fl
 
 // affine coupling (invertible_layer_glow.jl:110-116,121-129,142-157).  rb: (B, 2*C1, px) compact
 // pre-activation output Y3 of the ResidualBlock; x1: view of the C1 transformed channels.
+// ld_batch: the batch size the logdet is divided by (0: B; the HINT level pass runs on B * groups virtual samples)
 void op_coupling_fwd(Ctx& c, long long px, int B, int C1, View x1, View y1, const float* rb, float low,
-                     float high, double* ld);
+                     float high, double* ld, int ld_batch = 0);
 void op_coupling_inv(Ctx& c, long long px, int B, int C1, View y1, View x1, const float* rb, float low,
                      float high);
 // y1 -> x1, dy1 -> dx1 (views, in place allowed), rb (Y3) -> dY3 in place
