@@ -13,7 +13,8 @@ module InvertibleNetworksB200
 
 using CUDA
 using InvertibleNetworks
-import InvertibleNetworks: forward, inverse, backward, NetworkGlow, NetworkConditionalGlow, NetworkMultiScaleHINT, ActNorm,
+import InvertibleNetworks: forward, inverse, backward, NetworkGlow, NetworkConditionalGlow, NetworkMultiScaleHINT,
+                           CouplingLayerHINT, CouplingLayerBasic, ActNorm,
                            Conv1x1, CouplingLayerGlow, ResidualBlock, get_params, Parameter
 
 const LIB = get(ENV, "INB200_LIB", joinpath(@__DIR__, "..", "invertiblenetworks.jl_b200", "libinb200.so"))
@@ -307,6 +308,115 @@ function backward(ΔZ::CuArray{Float32}, Z::CuArray{Float32}, H::NetworkMultiSca
                 dptr(ΔX), dptr(X), stream()))
     assign_grads!(H, ps, fresh)   # H.CL[i,j].C is the Conv1x1 whose gradients accumulate (conv1x1.jl:237-239)
     return ΔX, X
+end
+
+# ---- layer level: CouplingLayerHINT (src/layers/invertible_layer_hint.jl:105-297) and CouplingLayerBasic
+# (src/layers/invertible_layer_basic.jl:90-149).  Reversed layers, permute = "both" and set_grad = false fall through.
+const PERMUTE = Dict("none" => Cint(0), "full" => Cint(1), "lower" => Cint(2))
+hint_on_b200(H::CouplingLayerHINT) = !H.is_reversed && haskey(PERMUTE, H.permute)
+function hint_ints(X::CuArray{Float32,N}, H::CouplingLayerHINT) where N
+    rb = H.CL[1].RB
+    act = H.CL[1].activation
+    nd = N - 2
+    return (Cint(nd), Cint(size(X, 1)), Cint(size(X, 2)), Cint(nd == 3 ? size(X, 3) : 1), Cint(size(X, N)),
+            Cint(size(X, N - 1)), Cint(size(rb.W2.data, N)), Cint(size(rb.W1.data, 1)), Cint(size(rb.W2.data, 1)),
+            Cfloat(act.low), Cfloat(act.high), PERMUTE[H.permute])
+end
+const HINT_ARGT = (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, Cfloat, Cint)
+
+# replaces :105-156 (scale = 1 entry; the recursion runs inside the library)
+function forward(X::CuArray{Float32,N}, H::CouplingLayerHINT; scale=1, permute=nothing, logdet=nothing) where N
+    (hint_on_b200(H) && scale == 1 && permute === nothing) ||
+        return invoke(forward, Tuple{AbstractArray{Float32,N},CouplingLayerHINT}, X, H; scale=scale, permute=permute, logdet=logdet)
+    logdet = logdet === nothing ? H.logdet : logdet
+    Y = similar(X)
+    ld = CUDA.zeros(Float32, 1)
+    check(ccall((:inb_hint_coupling_forward, LIB), Cint,
+                (HINT_ARGT..., Cint, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                hint_ints(X, H)..., PRECISION[], dptr(X), ptr_table(get_params(H), :data), dptr(Y),
+                logdet ? dptr(ld) : C_NULL, stream()))
+    logdet ? (return Y, Array(ld)[1]) : (return Y)
+end
+
+# replaces :159-204
+function inverse(Y::CuArray{Float32,N}, H::CouplingLayerHINT; scale=1, permute=nothing, logdet=nothing) where N
+    (hint_on_b200(H) && scale == 1 && permute === nothing && logdet !== true) ||
+        return invoke(inverse, Tuple{AbstractArray{Float32,N},CouplingLayerHINT}, Y, H; scale=scale, permute=permute, logdet=logdet)
+    X = similar(Y)
+    check(ccall((:inb_hint_coupling_inverse, LIB), Cint,
+                (HINT_ARGT..., Cint, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cvoid}),
+                hint_ints(Y, H)..., PRECISION[], dptr(Y), ptr_table(get_params(H), :data), dptr(X), stream()))
+    return X
+end
+
+# replaces :207-297 (set_grad = true)
+function backward(ΔY::CuArray{Float32,N}, Y::CuArray{Float32,N}, H::CouplingLayerHINT; scale=1, permute=nothing,
+                  set_grad::Bool=true) where N
+    (hint_on_b200(H) && scale == 1 && permute === nothing && set_grad) ||
+        return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},CouplingLayerHINT}, ΔY, Y, H;
+                      scale=scale, permute=permute, set_grad=set_grad)
+    ΔX, X = similar(Y), similar(Y)
+    ps = get_params(H)
+    fresh = [CUDA.zeros(Float32, size(p.data)) for p in ps]
+    check(ccall((:inb_hint_coupling_backward, LIB), Cint,
+                (HINT_ARGT..., Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat},
+                 Ptr{Cfloat}, Ptr{Cvoid}),
+                hint_ints(Y, H)..., Cint(H.logdet), HINT_SHARED_GRADS[], PRECISION[], dptr(ΔY), dptr(Y),
+                ptr_table(ps, :data), Ptr{Cfloat}[dptr(g) for g in fresh], dptr(ΔX), dptr(X), stream()))
+    hh = H.C === nothing ? Set{Parameter}() : Set{Parameter}((H.C.v1, H.C.v2, H.C.v3))
+    for (p, g) in zip(ps, fresh)   # Conv1x1 gradients accumulate unless cleared (conv1x1.jl:237-239)
+        p.grad = (p in hh && p.grad !== nothing) ? p.grad .+ g : g
+    end
+    return ΔX, X
+end
+
+# CouplingLayerBasic: forward :90-105, inverse :108-121, backward :124-149 (non-reversed, set_grad = true, save = false)
+function basic_ints(X1::CuArray{Float32,N}, L::CouplingLayerBasic) where N
+    rb = L.RB
+    nd = N - 2
+    return (Cint(nd), Cint(size(X1, 1)), Cint(size(X1, 2)), Cint(nd == 3 ? size(X1, 3) : 1), Cint(size(X1, N)),
+            Cint(size(X1, N - 1)), Cint(size(rb.W2.data, N)), Cint(size(rb.W1.data, 1)), Cint(size(rb.W2.data, 1)),
+            Cfloat(L.activation.low), Cfloat(L.activation.high))
+end
+const BASIC_ARGT = (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cfloat, Cfloat)
+function forward(X1::CuArray{Float32,N}, X2::CuArray{Float32,N}, L::CouplingLayerBasic; save::Bool=false, logdet=nothing) where N
+    (L.RB isa ResidualBlock && !save && !L.is_reversed) ||
+        return invoke(forward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},CouplingLayerBasic}, X1, X2, L; save=save, logdet=logdet)
+    logdet = logdet === nothing ? L.logdet : logdet
+    Y2 = similar(X2)
+    ld = CUDA.zeros(Float32, 1)
+    check(ccall((:inb_basic_coupling_forward, LIB), Cint,
+                (BASIC_ARGT..., Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                basic_ints(X1, L)..., PRECISION[], dptr(X1), dptr(X2), ptr_table(get_params(L), :data), dptr(Y2),
+                logdet ? dptr(ld) : C_NULL, stream()))
+    logdet ? (return X1, Y2, Array(ld)[1]) : (return X1, Y2)
+end
+function inverse(Y1::CuArray{Float32,N}, Y2::CuArray{Float32,N}, L::CouplingLayerBasic; save::Bool=false, logdet=nothing) where N
+    (L.RB isa ResidualBlock && !save && !L.is_reversed && logdet !== true) ||
+        return invoke(inverse, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},CouplingLayerBasic}, Y1, Y2, L; save=save, logdet=logdet)
+    X2 = similar(Y2)
+    check(ccall((:inb_basic_coupling_inverse, LIB), Cint,
+                (BASIC_ARGT..., Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cvoid}),
+                basic_ints(Y1, L)..., PRECISION[], dptr(Y1), dptr(Y2), ptr_table(get_params(L), :data), dptr(X2), stream()))
+    return Y1, X2
+end
+function backward(ΔY1::CuArray{Float32,N}, ΔY2::CuArray{Float32,N}, Y1::CuArray{Float32,N}, Y2::CuArray{Float32,N},
+                  L::CouplingLayerBasic; set_grad::Bool=true) where N
+    (L.RB isa ResidualBlock && set_grad && !L.is_reversed) ||
+        return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},AbstractArray{Float32,N},
+                                      AbstractArray{Float32,N},CouplingLayerBasic}, ΔY1, ΔY2, Y1, Y2, L; set_grad=set_grad)
+    ΔX1, ΔX2, X2 = similar(Y1), similar(Y2), similar(Y2)
+    ps = get_params(L)
+    fresh = [CUDA.zeros(Float32, size(p.data)) for p in ps]
+    check(ccall((:inb_basic_coupling_backward, LIB), Cint,
+                (BASIC_ARGT..., Cint, Cint, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Ptr{Cfloat}},
+                 Ptr{Ptr{Cfloat}}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
+                basic_ints(Y1, L)..., Cint(L.logdet), PRECISION[], dptr(ΔY1), dptr(ΔY2), dptr(Y1), dptr(Y2),
+                ptr_table(ps, :data), Ptr{Cfloat}[dptr(g) for g in fresh], dptr(ΔX1), dptr(ΔX2), dptr(X2), stream()))
+    for (p, g) in zip(ps, fresh)   # layer_residual_block.jl:168-172: overwritten
+        p.grad = g
+    end
+    return ΔX1, ΔX2, Y1, X2
 end
 
 # replaces wavelet_squeeze / wavelet_unsqueeze with type = WT.db1 and Haar_squeeze / invHaar_unsqueeze
