@@ -192,3 +192,42 @@ def test_hint_oracle_matches_golden():
     assert rel(Xr, X) < 1e-4
     for i, p in enumerate(ps):
         assert rel(p.grad, torch.from_numpy(gold[f"hint_g{i:03d}"])) < 1e-10, i
+
+
+@pytest.mark.parametrize("logdet", [True, False])
+def test_basic_coupling_properties(logdet):
+    """test_coupling_layer_basic.jl:12-66: forward -> inverse, forward -> backward (recompute), inverse -> forward, all to
+    atol 1e-2 there; plus float64 autograd of the hand-derived backward (:124-149)."""
+    torch.manual_seed(11)
+    gen = torch.Generator().manual_seed(11)
+    n_in, nh = 2, 4
+    RB = O.ResidualBlock(O.glorot_uniform(gen, nh, n_in, 3, 3, dtype=DT), O.glorot_uniform(gen, nh, nh, 3, 3, dtype=DT),
+                         O.glorot_uniform(gen, nh, 2 * n_in, 3, 3, dtype=DT), torch.zeros(nh, dtype=DT),
+                         torch.zeros(nh, dtype=DT), p1=1, p2=1)
+    L = H.CouplingLayerBasic(RB, logdet=logdet)
+    Xa, Xb = torch.randn(1, n_in, 24, 24, dtype=DT), torch.randn(1, n_in, 24, 24, dtype=DT)
+    Ya, Yb, ld = L.forward(Xa, Xb)
+    assert torch.equal(Ya, Xa)
+    assert rel(L.inverse(Ya, Yb)[1], Xb) < 1e-5
+    assert rel(L.backward(0 * Ya, 0 * Yb, Ya, Yb)[3], Xb) < 1e-5
+    Ya2, Yb2, _ = L.inverse(Xa, Xb)
+    assert rel(L.forward(Ya2, Yb2)[1], Xb) < 1e-5
+
+    def fwd(leaves):
+        Xa_l, Xb_l = leaves
+        Y1, Y2, ldl = L.forward(Xa_l, Xb_l)
+        f = 0.5 * (torch.sum(Y1 * Y1) + torch.sum(Y2 * Y2))
+        return f - ldl if logdet else f
+
+    Xal, Xbl = Xa.clone().requires_grad_(True), Xb.clone().requires_grad_(True)
+    ps = L.params()
+    leaves = [p.data.clone().requires_grad_(True) for p in ps]
+    for p, l in zip(ps, leaves):
+        p.data = l
+    ga = torch.autograd.grad(fwd((Xal, Xbl)), [Xal, Xbl] + leaves)
+    for p, l in zip(ps, leaves):
+        p.data = l.detach()
+    dXa, dXb, _, _ = L.backward(Ya.clone(), Yb.clone(), Ya, Yb)
+    assert rel(dXa, ga[0]) < 2e-5 and rel(dXb, ga[1]) < 2e-5
+    for p, g_auto in zip(ps, ga[2:]):
+        assert rel(p.grad, g_auto) < 1e-4
