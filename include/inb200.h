@@ -171,7 +171,7 @@ int inb_haar_unsqueeze(int nx, int ny, int B, int C, int type, const float* Y, f
 /* CouplingLayerHINT (invertible_layer_hint.jl:52-297) over CouplingLayerBasic (invertible_layer_basic.jl:62-149).
  * hparams = {CL[1].RB.(W1,W2,W3,b1,b2), ..., CL[n].RB.(...), [C.v1, C.v2, C.v3]} - the layer's get_params order,
  * n = inb_hint_depth(C) (get_depth, :63-71), the Conv1x1 entries present when permute != none; CL[j] acts on
- * C/2^j channels.  permute: 0 none, 1 full, 2 lower ("both" stays on the reference).
+ * C/2^j channels.  permute: 0 none, 1 full, 2 lower, 3 both.
  * shared_grads: a CL[j], j > 1, is applied 2^(j-1) times per pass; 0 = its gradient is the sum over the visits (the true
  * gradient; the reference's set_grad=false path, :222), 1 = only the last visit survives (what the reference's
  * set_grad=true path leaves in .grad, layer_residual_block.jl:168-172). */
@@ -192,6 +192,7 @@ int inb_basic_coupling_backward(int ndims, int nx, int ny, int nz, int B, int C1
 #define INB_PERMUTE_NONE 0
 #define INB_PERMUTE_FULL 1
 #define INB_PERMUTE_LOWER 2
+#define INB_PERMUTE_BOTH 3
 int inb_hint_depth(int C);
 int inb_hint_coupling_forward(int ndims, int nx, int ny, int nz, int B, int C, int nh, int k1, int k2, float low,
                               float high, int permute, int precision, const float* X, float* const* hparams,

@@ -85,7 +85,7 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
 // ---------------------------------------------------------------- HINT family (hint.cu)
 // CouplingLayerHINT (invertible_layer_hint.jl:52-300) over CouplingLayerBasic (invertible_layer_basic.jl:62-166),
 // all on channel-range views of ONE tensor (no tensor_split / tensor_cat copies).
-enum { HINT_PERMUTE_NONE = 0, HINT_PERMUTE_FULL = 1, HINT_PERMUTE_LOWER = 2 };
+enum { HINT_PERMUTE_NONE = 0, HINT_PERMUTE_FULL = 1, HINT_PERMUTE_LOWER = 2, HINT_PERMUTE_BOTH = 3 };
 struct HintShape {
   Geo g;
   int B, C, nh, k1, k2;

@@ -23,7 +23,7 @@ int HintShape::depth() const {
 
 void hint_check(const HintShape& h) {
   INB_CHECK(h.C >= 2, "CouplingLayerHINT needs at least 2 channels (got %d)", h.C);
-  INB_CHECK(h.permute >= 0 && h.permute <= 2, "permute must be none (0), full (1) or lower (2); 'both' stays on the reference");
+  INB_CHECK(h.permute >= 0 && h.permute <= 3, "permute must be none (0), full (1), lower (2) or both (3)");
   // Int(n_in/2^j) must be exact (hint.jl:86) and every level must split into equal halves
   const int n = h.depth();
   INB_CHECK(h.C % (1 << n) == 0 || (h.C <= 4 && h.C % 2 == 0),
@@ -148,7 +148,8 @@ static void rec_backward(Ctx& c, const HintShape& h, View dy, View y, int C, int
 
 void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& p, double* ld) {
   const long long px = h.g.px;
-  const bool full = h.permute == HINT_PERMUTE_FULL;
+  const bool both = h.permute == HINT_PERMUTE_BOTH;
+  const bool full = h.permute == HINT_PERMUTE_FULL || both;
   // [ActNorm (actnorm.jl:73)] + C.forward (hint.jl:111-113) in one pass; a plain copy when neither applies
   if (p.s || full)
     op_an_hh_fwd(c, px, h.B, h.C, x, y, p.s, p.b, full ? p.v1 : nullptr, full ? p.v2 : nullptr, full ? p.v3 : nullptr,
@@ -184,11 +185,14 @@ void hint_forward(Ctx& c, const HintShape& h, View x, View y, const HintParams& 
     rec_forward(c, h, y, h.C, 1, q, ld);
   }
   c.ar->release(m);
+  if (both) op_hh_an_inv(c, px, h.B, h.C, y, y, nullptr, nullptr, p.v1, p.v2, p.v3);  // Y = C.inverse(Y), :149
 }
 
 void hint_inverse(Ctx& c, const HintShape& h, View y, View x, const HintParams& p) {
   const long long px = h.g.px;
-  const bool full = h.permute == HINT_PERMUTE_FULL;
+  const bool both = h.permute == HINT_PERMUTE_BOTH;
+  const bool full = h.permute == HINT_PERMUTE_FULL || both;
+  if (both) op_an_hh_fwd(c, px, h.B, h.C, y, y, nullptr, nullptr, p.v1, p.v2, p.v3, nullptr);  // Y = C.forward(Y), :164
   {
     size_t m = c.ar->mark();
     std::vector<PackedW> store;
@@ -210,8 +214,21 @@ void hint_inverse(Ctx& c, const HintShape& h, View y, View x, const HintParams& 
 void hint_backward(Ctx& c, const HintShape& h, View dy, View y, View dx, View x, const HintParams& p,
                    const HintGrads& g) {
   const long long px = h.g.px;
-  const bool full = h.permute == HINT_PERMUTE_FULL, lower = h.permute == HINT_PERMUTE_LOWER;
+  const bool both = h.permute == HINT_PERMUTE_BOTH;
+  const bool full = h.permute == HINT_PERMUTE_FULL || both, lower = h.permute == HINT_PERMUTE_LOWER;
   size_t m = c.ar->mark();
+  float* tv = nullptr;  // gradient of C through its second use (Y = C.inverse(Y) at the end of forward), as (v3, v2, v1)
+  if (both) {
+    // dY, Y = C.forward((dY, Y)), hint.jl:219-221.  The map undone here is Z = Y * H3 H2 H1 - a Conv1x1 whose vectors are
+    // (v3, v2, v1) - so its (dZ, Z) -> (dY, Y) step and its Householder gradients are the inverse-tuple kernels with the
+    // vectors in reverse order (equal to conv1x1_grad_v(.; adjoint = true), conv1x1.jl:196, asserted against autograd
+    // in tests/test_oracle_hint.py); the two contributions to C's gradients are summed below (conv1x1.jl:198-200).
+    double* gram2 = c.ar->f64((size_t)h.C * h.C);
+    tv = c.ar->f32(3 * (size_t)h.C);
+    op_zero(c, gram2, (size_t)h.C * h.C * sizeof(double));
+    op_hh_an_bwd(c, px, h.B, h.C, dy, y, dy, y, nullptr, nullptr, p.v3, p.v2, p.v1, gram2, nullptr);
+    op_hh_grad_finish(c, h.C, gram2, p.v3, p.v2, p.v1, 0, tv, tv + h.C, tv + 2 * h.C);
+  }
   std::vector<char> seen(p.cl.size(), 0);
   std::vector<PackedW> store;
   const HintParams q = hint_prepack(c, h, p, true, store);
@@ -229,6 +246,12 @@ void hint_backward(Ctx& c, const HintShape& h, View dy, View y, View dx, View x,
     op_hh_an_bwd(c, px, h.B, h.C, dy, y, dx, x, p.s, p.b, full ? p.v1 : nullptr, full ? p.v2 : nullptr,
                  full ? p.v3 : nullptr, full ? gram : nullptr, p.s ? dsdb : nullptr);
     if (full) op_hh_grad_finish(c, h.C, gram, p.v1, p.v2, p.v3, 0, g.v1, g.v2, g.v3);
+    if (both) {
+      const float* src[3] = {tv + 2 * h.C, tv + h.C, tv};
+      float* dst[3] = {g.v1, g.v2, g.v3};
+      const long long n[3] = {h.C, h.C, h.C};
+      op_accum(c, 3, src, dst, n);
+    }
     if (p.s) op_an_grad_finish(c, h.C, px, dsdb, p.s, h.logdet, g.s, g.b);
   } else {
     if (x.p != y.p) op_copy(c, px, h.B, h.C, y, x);

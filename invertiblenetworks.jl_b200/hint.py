@@ -126,20 +126,20 @@ class CouplingLayerBasic:
 
 class CouplingLayerHINT:
     """H = CouplingLayerHINT(n_in, n_hidden; logdet, permute, k1, k2, p1, p2, activation=SigmoidLayer(low, high))
-    invertible_layer_hint.jl:78-101.  permute in {"none", "full", "lower"}."""
+    invertible_layer_hint.jl:78-101.  permute in {"none", "full", "lower", "both"}."""
 
     def __init__(self, n_in: int, n_hidden: int, *, logdet=False, permute="none", k1=3, k2=3, p1=1, p2=1, ndims=2,
                  low=0.0, high=1.0, shared_grads="sum", precision="fp32", gen: Optional[torch.Generator] = None,
                  device="cuda"):
-        if permute == "both":
-            raise _l.InbError("permute='both' is not on the B200 path")
+        if permute not in _l.PERMUTES:
+            raise _l.InbError(f"unknown permute mode {permute!r}")
         if p1 != (k1 - 1) // 2 or p2 != (k2 - 1) // 2:
             raise _l.InbError("only 'same' padding is supported on the B200 path")
         gen = gen or torch.Generator().manual_seed(0)
         self.n_in, self.n_hidden, self.logdet, self.permute = n_in, n_hidden, logdet, permute
         self.k1, self.k2, self.ndims, self.low, self.high = k1, k2, ndims, low, high
         self.shared_grads, self.precision = shared_grads, _l.PRECISIONS[precision]
-        nconv = {"none": 0, "full": n_in, "lower": n_in // 2}[permute]
+        nconv = {"none": 0, "full": n_in, "lower": n_in // 2, "both": n_in}[permute]
         shapes = _hint_shapes(n_in, n_hidden, k1, k2, ndims, nconv)
         self._params = []
         for i, s in enumerate(shapes):

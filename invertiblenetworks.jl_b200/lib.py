@@ -36,7 +36,7 @@ class HintDesc(C.Structure):
 
 
 SQUEEZE_TYPES = {"wavelet": 0, "haar": 1}
-PERMUTES = {"none": 0, "full": 1, "lower": 2}
+PERMUTES = {"none": 0, "full": 1, "lower": 2, "both": 3}
 SHARED_GRADS = {"sum": 0, "last": 1}
 
 P = C.c_void_p      # device pointer / stream / plan

@@ -311,8 +311,8 @@ function backward(ΔZ::CuArray{Float32}, Z::CuArray{Float32}, H::NetworkMultiSca
 end
 
 # ---- layer level: CouplingLayerHINT (src/layers/invertible_layer_hint.jl:105-297) and CouplingLayerBasic
-# (src/layers/invertible_layer_basic.jl:90-149).  Reversed layers, permute = "both" and set_grad = false fall through.
-const PERMUTE = Dict("none" => Cint(0), "full" => Cint(1), "lower" => Cint(2))
+# (src/layers/invertible_layer_basic.jl:90-149).  Reversed layers and set_grad = false fall through.
+const PERMUTE = Dict("none" => Cint(0), "full" => Cint(1), "lower" => Cint(2), "both" => Cint(3))
 hint_on_b200(H::CouplingLayerHINT) = !H.is_reversed && haskey(PERMUTE, H.permute)
 function hint_ints(X::CuArray{Float32,N}, H::CouplingLayerHINT) where N
     rb = H.CL[1].RB

@@ -296,8 +296,9 @@ class Conv1x1:
         """conv1x1.jl:209-224 : X_i = Y_i H3 H2 H1."""
         return chain_lr(self._flat(Y), self.v3.data, self.v2.data, self.v1.data).reshape(Y.shape)
 
-    def grad_v(self, X: Tensor, dY: Tensor, faithful_batch_loop: bool = True):
-        """conv1x1.jl:118-170 (adjoint=false branch, the one `inverse(::Tuple)` uses)."""
+    def grad_v(self, X: Tensor, dY: Tensor, faithful_batch_loop: bool = True, adjoint: bool = False):
+        """conv1x1.jl:118-170; adjoint=false is what `inverse(::Tuple)` uses (:234), adjoint=true what
+        `forward(::Tuple)` uses (:196): every dV_j[i] is transposed (:150,154,157)."""
         v1, v2, v3 = self.v1.data, self.v2.data, self.v3.data
         k = self.k
         if self.freeze:  # :132-134
@@ -315,6 +316,8 @@ class Conv1x1:
             t = dV2[i]
             dV2[i] = t + (4 * V1 @ t @ V3 - 2 * (V1 @ t + t @ V3))
             dV3[i] = M3 @ dV3[i]
+            if adjoint:
+                dV1[i], dV2[i], dV3[i] = dV1[i].T.clone(), dV2[i].T.clone(), dV3[i].T.clone()
         Xf, dYf = self._flat(X), self._flat(dY)
         dv = [torch.zeros_like(v1) for _ in range(3)]
         if faithful_batch_loop:
@@ -331,6 +334,15 @@ class Conv1x1:
             for j, dV in enumerate((dV1, dV2, dV3)):
                 dv[j] = torch.einsum("ikl,kl->i", dV, G)
         return dv[0], dv[1], dv[2]
+
+    def forward_tuple(self, dX: Tensor, X: Tensor, faithful_batch_loop: bool = True):
+        """conv1x1.jl:191-205 : (ΔY, Y) = (forward(ΔX), forward(X)), Δv from (Y, ΔX) with adjoint=true, accumulated."""
+        dY = self.forward(dX)
+        Y = self.forward(X)
+        d1, d2, d3 = self.grad_v(Y, dX, faithful_batch_loop, adjoint=True)
+        for p, d in ((self.v1, d1), (self.v2, d2), (self.v3, d3)):
+            p.grad = d if p.grad is None else p.grad + d
+        return dY, Y
 
     def inverse_tuple(self, dY: Tensor, Y: Tensor, faithful_batch_loop: bool = True):
         """conv1x1.jl:227-245 : (ΔX, X) and accumulate Δv (+= when already set, :237-239)."""

@@ -187,7 +187,7 @@ def get_depth(n_in: int) -> int:
 class CouplingLayerHINT:
     def __init__(self, CL: Sequence[CouplingLayerBasic], C: Optional[Conv1x1], logdet: bool = False,
                  permute: str = "none", shared_grads: str = "sum"):
-        assert permute in ("none", "full", "lower"), "permute='both' is not restated"
+        assert permute in ("none", "full", "lower", "both")
         assert shared_grads in ("sum", "last")
         self.CL, self.C, self.logdet, self.permute, self.shared_grads = list(CL), C, logdet, permute, shared_grads
 
@@ -203,7 +203,7 @@ class CouplingLayerHINT:
     # :105-156
     def forward(self, X: Tensor, scale: int = 1, permute: Optional[str] = None):
         permute = self.permute if permute is None else permute
-        if permute == "full":
+        if permute in ("full", "both"):  # :111-113
             X = self.C.forward(X)
         Xa, Xb = tensor_split(X)
         if permute == "lower":
@@ -217,11 +217,16 @@ class CouplingLayerHINT:
         else:
             Ya = Xa.clone()
             _, Yb, ld = cl.forward(Xa, Xb)
-        return tensor_cat(Ya, Yb), ld
+        Y = tensor_cat(Ya, Yb)
+        if permute == "both":  # :149
+            Y = self.C.inverse(Y)
+        return Y, ld
 
     # :159-204
     def inverse(self, Y: Tensor, scale: int = 1, permute: Optional[str] = None) -> Tensor:
         permute = self.permute if permute is None else permute
+        if permute == "both":  # :164
+            Y = self.C.forward(Y)
         Ya, Yb = tensor_split(Y)
         cl = self.CL[scale - 1]
         if Y.shape[1] > 4:
@@ -234,7 +239,7 @@ class CouplingLayerHINT:
         if permute == "lower":
             Xb = self.C.inverse(Xb)
         X = tensor_cat(Xa, Xb)
-        if permute == "full":
+        if permute in ("full", "both"):  # :195-197
             X = self.C.inverse(X)
         return X
 
@@ -252,6 +257,8 @@ class CouplingLayerHINT:
     def backward(self, dY: Tensor, Y: Tensor, scale: int = 1, permute: Optional[str] = None, seen=None):
         permute = self.permute if permute is None else permute
         seen = set() if seen is None else seen
+        if permute == "both":  # :219-221
+            dY, Y = self.C.forward_tuple(dY, Y, faithful_batch_loop=False)
         Ya, Yb = tensor_split(Y)
         dYa, dYb = tensor_split(dY)
         cl = self.CL[scale - 1]
@@ -268,7 +275,7 @@ class CouplingLayerHINT:
         if permute == "lower":
             dXb, Xb = self.C.inverse_tuple(dXb, Xb, faithful_batch_loop=False)  # :268
         dX, X = tensor_cat(dXa, dXb), tensor_cat(Xa, Xb)
-        if permute == "full":
+        if permute in ("full", "both"):
             dX, X = self.C.inverse_tuple(dX, X, faithful_batch_loop=False)  # :278
         return dX, X
 
@@ -287,7 +294,7 @@ def make_hint_coupling(gen, n_in: int, n_hidden: int, *, logdet=False, permute="
                            glorot_uniform(gen, n_hidden, 2 * c, k1, k1, dtype=dtype),
                            torch.zeros(n_hidden, dtype=dtype), torch.zeros(n_hidden, dtype=dtype), p1=p1, p2=p2)
         cls.append(CouplingLayerBasic(RB, logdet=logdet, low=low, high=high))
-    if permute == "full":
+    if permute in ("full", "both"):
         C = Conv1x1(*(glorot_uniform(gen, n_in, dtype=dtype) for _ in range(3)))
     elif permute == "lower":
         C = Conv1x1(*(glorot_uniform(gen, n_in // 2, dtype=dtype) for _ in range(3)))

@@ -64,7 +64,7 @@ def _autograd_check(layer_params, run_forward, X0, hand):
 
 
 @pytest.mark.parametrize("C", [4, 8, 16])
-@pytest.mark.parametrize("permute", ["none", "full", "lower"])
+@pytest.mark.parametrize("permute", ["none", "full", "lower", "both"])
 @pytest.mark.parametrize("logdet", [False, True])
 def test_hint_coupling_invertibility_and_autograd(C, permute, logdet):
     torch.manual_seed(C)
