@@ -9,7 +9,8 @@ from . import lib
 from . import dp
 from .lib import InbError, PRECISIONS
 from .glow import (ADAM, ActNorm, Conv1x1, CouplingLayerGlow, NetworkConditionalGlow, NetworkGlow, NetworkGlow3D,
-                   Parameter, ResidualBlock, clear_grad, get_grads, get_params, nll_grad, set_params, squeeze,
+                   Parameter, ResidualBlock, clear_grad, get_grads, get_params, load_params, nll_grad, save_params,
+                   set_params, squeeze,
                    unsqueeze)
 
 from .hint import (CouplingLayerBasic, CouplingLayerHINT, Haar_squeeze, NetworkMultiScaleHINT, get_depth, invHaar_unsqueeze,
@@ -20,6 +21,6 @@ ConditionalLayerGlow = CouplingLayerGlow  # same class with n_cond > 0 (conditio
 __all__ = [
     "ADAM", "ActNorm", "Conv1x1", "CouplingLayerGlow", "ConditionalLayerGlow", "NetworkConditionalGlow", "NetworkGlow",
     "NetworkGlow3D", "Parameter", "ResidualBlock", "clear_grad", "get_grads", "get_params", "nll_grad",
-    "set_params", "squeeze", "unsqueeze", "CouplingLayerBasic", "CouplingLayerHINT", "NetworkMultiScaleHINT", "Haar_squeeze",
+    "set_params", "save_params", "load_params", "squeeze", "unsqueeze", "CouplingLayerBasic", "CouplingLayerHINT", "NetworkMultiScaleHINT", "Haar_squeeze",
     "invHaar_unsqueeze", "wavelet_squeeze", "wavelet_unsqueeze", "get_depth", "InbError", "PRECISIONS", "lib", "dp",
 ]

@@ -65,6 +65,33 @@ def set_params(obj, new: Sequence) -> None:
         obj._mark_initialized()
 
 
+def save_params(obj, path: str) -> None:
+    """Checkpoint in get_params order (the Julia side keeps `BSON.@save "net.bson" get_params(G) |> cpu`
+    of examples/utils/save_load_network.jl:24-26 unchanged, because the shim never touches the Parameter containers).
+    Here: one .npz with arrays p000, p001, ... in get_params order, stored in the REFERENCE's axis order - a torch tensor
+    (Cout, Cin, ky, kx) is written as the Julia array (kx, ky, Cin, Cout), so `NPZ.npzread` + `set_params!` loads it."""
+    import numpy as np
+    arrs = {}
+    for i, p in enumerate(obj.get_params()):
+        a = p.data.detach().cpu().numpy()
+        arrs[f"p{i:03d}"] = np.ascontiguousarray(a.transpose(*reversed(range(a.ndim))))
+    np.savez(path, **arrs)
+
+
+def load_params(obj, path: str) -> None:
+    """Inverse of save_params (set_params! semantics: shapes must match the architecture)."""
+    import numpy as np
+    z = np.load(path)
+    ps = obj.get_params()
+    if len(z.files) != len(ps):
+        raise ValueError(f"checkpoint holds {len(z.files)} parameters, the network {len(ps)}")
+    new = []
+    for i in range(len(ps)):
+        a = z[f"p{i:03d}"]
+        new.append(torch.from_numpy(np.ascontiguousarray(a.transpose(*reversed(range(a.ndim))))))
+    set_params(obj, new)
+
+
 def _check(x: Tensor, name="X") -> Tensor:
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise _l.InbError(f"{name}: the B200 path takes CUDA tensors only (no CPU fallback)")

@@ -280,3 +280,23 @@ def test_full_size_cfg5_3d_and_cfg3_conditional_properties():
     assert rel(C.inverse(ZX, ZC), Xc) < 1e-5
     out = C.backward(ZX / 8, ZX, ZC)
     assert rel(out[1], Xc) < 1e-5 and torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+
+
+def test_checkpoint_roundtrip_in_get_params_order(tmp_path):
+    """save_params / load_params: a second network of the same architecture loaded from the file
+    gives bit-identical outputs; arrays are stored in the reference's axis order."""
+    import numpy as np
+    torch.manual_seed(4)
+    X = torch.rand(2, 2, 16, 16, device=DEV)
+    G = inb200.NetworkGlow(2, 8, 2, 2, split_scales=True, device=DEV, seed=1)
+    Z, ld = G.forward(X)  # initialises ActNorm
+    path = str(tmp_path / "net_params.npz")
+    inb200.save_params(G, path)
+    z = np.load(path)
+    assert len(z.files) == len(G.get_params())
+    W1 = G.get_params()[2 * 2 * 2 + 3].data  # CL[1,1].RB.W1, torch (nh, Cin, ky, kx)
+    assert z[f"p{2 * 2 * 2 + 3:03d}"].shape == tuple(reversed(W1.shape))  # Julia (kx, ky, Cin, nh)
+    G2 = inb200.NetworkGlow(2, 8, 2, 2, split_scales=True, device=DEV, seed=99)
+    inb200.load_params(G2, path)
+    Z2, ld2 = G2.forward(X)
+    assert torch.equal(Z, Z2) and torch.equal(ld, ld2)
