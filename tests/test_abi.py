@@ -152,3 +152,35 @@ def test_host_mirror_param_shapes_match_oracle():
     Oc = O.NetworkConditionalGlow(1, 2, 8, 2, 2, split_scales=True)
     for p, q in zip(Gc.get_params()[10:], Oc.get_params()[10:]):
         assert tuple(p.data.shape) == tuple(q.data.shape)
+
+
+def test_product_path_never_touches_the_oracle_and_has_no_fallback():
+    """The oracle is test infrastructure: nothing under invertiblenetworks.jl_b200/ may import, call or mention it, and
+    a missing libinb200.so is a hard error (no CPU / PyTorch fallback)."""
+    pkg = os.path.join(ROOT, "invertiblenetworks.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "build":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "/root/reference" not in src, f"{f} reads the reference tree"
+                if f.endswith(".py"):
+                    assert not re.search(r"^\s*(from|import)\s+\.*oracle|oracle\.|import_module\([^)]*oracle", src, flags=re.M), \
+                        f"{f} imports or calls the oracle"
+    saved, L._lib = L._lib, None
+    real = L.LIB_PATH
+    try:
+        L.LIB_PATH = os.path.join(pkg, "no_such_library.so")
+        with pytest.raises(L.InbError, match="no CPU or PyTorch fallback"):
+            L.load()
+    finally:
+        L.LIB_PATH, L._lib = real, saved
+
+
+def test_hint_host_mirror_refuses_cpu_tensors():
+    H = inb200.CouplingLayerHINT(8, 4, device="cpu")
+    with pytest.raises(L.InbError, match="CUDA tensors only"):
+        H.forward(torch.randn(1, 8, 4, 4))
+    with pytest.raises(L.InbError, match="CUDA tensors only"):
+        inb200.wavelet_squeeze(torch.randn(1, 1, 4, 4))
