@@ -231,3 +231,22 @@ def test_basic_coupling_properties(logdet):
     assert rel(dXa, ga[0]) < 2e-5 and rel(dXb, ga[1]) < 2e-5
     for p, g_auto in zip(ps, ga[2:]):
         assert rel(p.grad, g_auto) < 1e-4
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_hint_host_mirror_param_shapes_match_oracle(split):
+    """The Python mirror's flat parameter buffer (get_params order, torch layout) against the oracle's containers."""
+    net = inb200.NetworkMultiScaleHINT(2, 6, 3, 2, split_scales=split, device="cpu")
+    ora = H.NetworkMultiScaleHINT(2, 6, 3, 2, split_scales=split)
+    ps, qs = net.get_params(), ora.get_params()
+    assert len(ps) == len(qs)
+    n_an = 2 * 3 * 2
+    for i, (p, q) in enumerate(zip(ps, qs)):
+        if i < n_an:
+            assert q.data is None and p.data.numel() == ora.AN[i // 4][(i // 2) % 2].k
+        else:
+            assert tuple(p.data.shape) == tuple(q.data.shape), i
+    for permute in ("none", "full", "lower", "both"):
+        HL = inb200.CouplingLayerHINT(16, 5, permute=permute, device="cpu")
+        OL = H.make_hint_coupling(torch.Generator().manual_seed(0), 16, 5, permute=permute)
+        assert [tuple(p.data.shape) for p in HL.get_params()] == [tuple(p.data.shape) for p in OL.params()]
