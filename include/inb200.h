@@ -40,6 +40,10 @@ extern "C" {
 #define INB_PREC_FP32 0        /* fp32 FMA on CUDA cores: bit-for-bit fp32 arithmetic        */
 #define INB_PREC_BF16X3 1      /* tcgen05 bf16 tensor cores, 3-term split (fp32-equivalent)  */
 #define INB_PREC_BF16 2        /* tcgen05 bf16 tensor cores, single pass, fp32 accumulate    */
+#define INB_PREC_FP16X3 3      /* tcgen05 kind::f16 with IEEE-half operands, 3-term split: 2 x 11 significant bits per
+                                  operand (float32-level products) at the bf16x3 rate; weights and gradients are
+                                  pre-scaled by exact powers of two (the gradient scale is derived on the device from
+                                  max|dY| of each ResidualBlock backward).  Needs the fused chain (k2 = 1, n_hidden 128 / 256). */
 
 typedef struct inb_plan inb_plan;
 
@@ -92,6 +96,40 @@ int inb_glow_inverse(inb_plan* plan, int batch, const float* Z, float* const* pa
  * Writes dX, X (recomputed by inversion) and every gradient in `grads` (get_params order). */
 int inb_glow_backward(inb_plan* plan, int batch, const float* dZ, const float* Z,
                       float* const* params, float* const* grads, float* dX, float* X, void* stream);
+
+/* ------------------------------------------------------------------ data-parallel training
+ * One process per GPU, the batch sharded along its outermost dimension, parameters replicated.  The reference has no
+ * multi-GPU path of its own; these entry points are what a Julia caller binds next to NCCL.jl / MPI.jl.
+ * NCCL is resolved at run time (dlopen of libnccl.so.2, preferring the instance already loaded by the host framework;
+ * INB200_NCCL_LIB overrides); a process that never calls these needs no NCCL.
+ *
+ * Canonical flat layout: offsets[i] = element offset of parameter i (get_params order) in ONE buffer of `total` floats,
+ * every tensor on a 256-byte boundary.  A caller that keeps its gradients (and parameters) in such a buffer gets one
+ * collective per contiguous range instead of one per tensor. */
+typedef struct inb_comm inb_comm;
+int inb_glow_flat_layout(const inb_plan* plan, long long* offsets /* [num_params], nullable */, long long* total);
+/* rank 0 calls inb_comm_unique_id and ships the 128 bytes to the other ranks by any means (MPI.bcast, a file, torch's
+ * store); every rank then calls inb_comm_create on its own device (ncclCommInitRank). */
+int inb_comm_unique_id(char id[128]);
+int inb_comm_create(int nranks, int rank, const char id[128], inb_comm** comm);
+/* wrap an existing ncclComm_t (NCCL.jl: Communicator.handle; torch: ProcessGroupNCCL._comm_ptr()); not destroyed with the handle */
+int inb_comm_wrap(void* nccl_comm, inb_comm** comm);
+int inb_comm_destroy(inb_comm* comm);
+int inb_comm_info(const inb_comm* comm, int* nranks, int* rank, long long* allreduce_calls, long long* allreduce_bytes);
+/* Attach a communicator to a plan (NULL detaches).  With a communicator attached
+ *  - inb_glow_forward / inb_cglow_forward with init_actnorm != 0 initialise every ActNorm from the statistics of the
+ *    GLOBAL batch (per layer: all-reduce of the per-shard sums, then of the squared deviations from the global mean =
+ *    invertible_layer_actnorm.jl:67-72 on the concatenated shards), so every rank ends with identical s, b;
+ *  - inb_glow_backward / inb_cglow_backward average the gradients over the ranks: as soon as the flow steps of a scale
+ *    are done its 10*K tensors are all-reduced (ncclAvg) on the communicator's own stream, overlapped with the
+ *    remaining scales; the call's stream waits for the last collective before it returns control to later work.
+ *    Averaging the per-shard gradients of f = ||Z||^2/(2B) - logdet reproduces the single-process gradient of the
+ *    global batch (the only batch-independent term, ActNorm's prod(spatial)*sum(log|s|), is invariant under averaging). */
+int inb_glow_plan_set_comm(inb_plan* plan, inb_comm* comm);
+/* the same average as one explicit call (all tensors of `grads`, on `stream`) for callers that do not attach */
+int inb_allreduce_grads(inb_plan* plan, float* const* grads, inb_comm* comm, void* stream);
+/* every rank receives rank `root`'s parameters */
+int inb_broadcast_params(inb_plan* plan, float* const* params, inb_comm* comm, int root, void* stream);
 
 /* NetworkConditionalGlow (invertible_network_conditional_glow.jl:107-181).  forward returns
  * ZX (X's shape), ZC (the ActNorm'ed condition squeezed L times when split_scales) and logdet;

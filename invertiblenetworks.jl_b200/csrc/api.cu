@@ -2,6 +2,7 @@
 // and the network drivers that walk the L x K flow steps inside the library.
 #include "../../include/inb200.h"
 #include "glow.cuh"
+#include "dp.cuh"
 #include <mutex>
 #include <vector>
 
@@ -144,13 +145,70 @@ struct inb_plan : GraphCache {
   size_t need = 0;     // workspace bytes (sizing pass at plan creation)
   double* ld = nullptr;
   SideLane lane;
+  DpComm* dp = nullptr;  // attached communicator (inb_glow_plan_set_comm), not owned
+  std::vector<long long> numel;     // element count of every parameter (get_params order)
+  std::vector<long long> flat_off;  // canonical flat layout: element offset of every parameter, 64-element aligned
+  long long flat_total = 0;
 };
+struct inb_comm : inb::DpComm {};
+namespace inb {
+void dp_unique_id(char* id128);
+DpComm* dp_create(int nranks, int rank, const char* id128);
+DpComm* dp_wrap(void* nccl_comm);
+void dp_destroy(DpComm* dp);
+void dp_broadcast_f32(DpComm* dp, float* const* ptrs, const long long* numel, int n, long long max_gap, int root,
+                      cudaStream_t st);
+}
 
 static int an_index(const inb_plan* p, int i, int j, int which) { return 2 * (i * p->d.K + j) + which; }
 static int cl_index(const inb_plan* p, int i, int j, int which) {
   return 2 * p->d.L * p->d.K + (p->cond ? 2 : 0) + 8 * (i * p->d.K + j) + which;
 }
 static int anc_index(const inb_plan* p, int which) { return 2 * p->d.L * p->d.K + which; }
+
+// element count of parameter `index` (get_params order)
+static long long plan_param_numel(const inb_plan* p, int index) {
+  const int LK = p->d.L * p->d.K;
+  if (index < 2 * LK) return p->sc[(index / 2) / p->d.K].C;
+  index -= 2 * LK;
+  if (p->cond) {
+    if (index < 2) return p->d.n_cond;
+    index -= 2;
+  }
+  const int layer = index / 8, which = index % 8;
+  const ScaleInfo& s = p->sc[layer / p->d.K];
+  const int C1 = split_k(s.C), nh = p->d.n_hidden;
+  const int Cin = s.C - C1 + (p->cond ? s.Ccond : 0), Cout = 2 * C1;
+  long long t1 = 1, t2 = 1;
+  for (int a = 0; a < p->d.ndims; ++a) { t1 *= p->d.k1; t2 *= p->d.k2; }
+  switch (which) {
+    case 0: case 1: case 2: return s.C;
+    case 3: return t1 * Cin * nh;
+    case 4: return t2 * nh * nh;
+    case 5: return t1 * Cout * nh;
+    default: return nh;
+  }
+}
+static void plan_layout(inb_plan* p) {
+  const int n = 10 * p->d.L * p->d.K + (p->cond ? 2 : 0);
+  p->numel.resize(n);
+  p->flat_off.resize(n);
+  long long o = 0;
+  for (int i = 0; i < n; ++i) {
+    p->numel[i] = plan_param_numel(p, i);
+    p->flat_off[i] = o;
+    o += (p->numel[i] + 63) / 64 * 64;  // every tensor starts on a 256-byte boundary
+  }
+  p->flat_total = o;
+}
+// the caller's table follows the canonical flat layout (inb_glow_flat_layout): the gaps between consecutive tensors are
+// the caller's own alignment padding and a bucket may be reduced as one range across them
+static long long table_max_gap(const inb_plan* p, float* const* t) {
+  for (size_t i = 0; i < p->flat_off.size(); ++i)
+    if (t[i] != t[0] + p->flat_off[i]) return 0;
+  return 63;
+}
+
 
 static void plan_scales(inb_plan* p) {
   const inb_glow_desc& d = p->d;
@@ -435,6 +493,14 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
       c.lane->wait_deferred(c.st, 1);
     }
     c.ar->release(mpack);
+    if (grads && gr && c.dp && c.dp->nranks > 1 && !c.dry()) {
+      // data parallel: this scale's 10*K gradients are final - average them over the ranks on the
+      // communicator's stream while the remaining scales run (two ranges when the caller's table is the flat layout)
+      dp_fork(c.dp, c.st, (c.lane && c.lane->used) ? c.lane->st : nullptr);
+      const long long gap = table_max_gap(p, gr);
+      dp_allreduce_avg_bucket(c.dp, gr, p->numel.data(), an_index(p, i, 0, 0), 2 * d.K, gap, c.dp->st);
+      dp_allreduce_avg_bucket(c.dp, gr, p->numel.data(), cl_index(p, i, 0, 0), 8 * d.K, gap, c.dp->st);
+    }
     if (d.split_scales) {  // :186-187 unsqueeze
       Geo gout = (i == 0) ? p->g0 : make_geo(d.ndims, s.g.W * 2, s.g.H * 2, s.g.D * 2);
       int cout = s.C >> d.ndims;
@@ -475,7 +541,12 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
     op_an_grad_finish(c, d.n_cond, p->g0.px, dsdb, s, 0, gr ? gr[anc_index(p, 0)] : nullptr,
                       gr ? gr[anc_index(p, 1)] : nullptr);
     c.ar->release(m2);
+    if (gr && c.dp && c.dp->nranks > 1 && !c.dry()) {
+      dp_fork(c.dp, c.st, nullptr);
+      dp_allreduce_avg_bucket(c.dp, gr, p->numel.data(), anc_index(p, 0), 2, table_max_gap(p, gr), c.dp->st);
+    }
   }
+  if (c.dp && !c.dry()) dp_join(c.dp, c.st);  // the averaged gradients belong to this call
   if (c.lane) c.lane->join(c.st);  // the gradient kernels on the side lane belong to this call
   c.ar->release(m);
 }
@@ -491,7 +562,7 @@ static void check_desc(const inb_glow_desc* d) {
             "supported ResidualBlock kernel sizes are 1 and 3 (got k1=%d k2=%d)", d->k1, d->k2);
   INB_CHECK(d->p1 == (d->k1 - 1) / 2 && d->p2 == (d->k2 - 1) / 2,
             "only 'same' padding is supported (p = (k-1)/2; got p1=%d p2=%d)", d->p1, d->p2);
-  INB_CHECK(d->precision >= 0 && d->precision <= 2, "unknown precision mode %d", d->precision);
+  INB_CHECK(d->precision >= 0 && d->precision <= 3, "unknown precision mode %d", d->precision);
   INB_CHECK(d->sig_high > d->sig_low, "sigmoid high must exceed low");
 }
 
@@ -545,6 +616,7 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
     p->lane.wpending[0] = p->lane.wpending[1] = false;
     c.lane = &p->lane;
   }
+  c.dp = p->dp;
   return c;
 }
 
@@ -556,6 +628,7 @@ static uint64_t mix(uint64_t h, uint64_t v) {
 static uint64_t key_of(const inb_plan* p, int batch, std::initializer_list<const void*> ptrs, float* const* params,
                        float* const* grads) {
   uint64_t h = mix(0x1234567ull, (uint64_t)batch);
+  h = mix(h, (uint64_t)(uintptr_t)p->dp);  // a graph captured with a communicator holds its collectives
   for (const void* q : ptrs) h = mix(h, (uint64_t)(uintptr_t)q);
   const int n = 10 * p->d.L * p->d.K + (p->cond ? 2 : 0);
   for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)params[i]);
@@ -663,6 +736,7 @@ int inb_glow_plan_create(const inb_glow_desc* desc, inb_plan** out) {
     p->cond = p->d.n_cond > 0;
     if (p->cond) p->d.logdet = 1;  // the conditional network always carries logdet (:107-130)
     plan_scales(p.get());
+    plan_layout(p.get());
     // sizing pass
     Arena dry;
     dry.dry = true;
@@ -714,30 +788,17 @@ int inb_glow_num_params(const inb_plan* p) {
 int inb_glow_param_numel(const inb_plan* p, int index, long long* numel) {
   return guarded([&] {
     INB_CHECK(p && numel, "null argument");
-    const int LK = p->d.L * p->d.K;
     INB_CHECK(index >= 0 && index < inb_glow_num_params(p), "parameter index %d out of range", index);
-    if (index < 2 * LK) {
-      *numel = p->sc[(index / 2) / p->d.K].C;
-      return;
-    }
-    index -= 2 * LK;
-    if (p->cond) {
-      if (index < 2) { *numel = p->d.n_cond; return; }
-      index -= 2;
-    }
-    const int layer = index / 8, which = index % 8;
-    const ScaleInfo& s = p->sc[layer / p->d.K];
-    const int C1 = split_k(s.C), nh = p->d.n_hidden;
-    const int Cin = s.C - C1 + (p->cond ? s.Ccond : 0), Cout = 2 * C1;
-    long long t1 = 1, t2 = 1;
-    for (int a = 0; a < p->d.ndims; ++a) { t1 *= p->d.k1; t2 *= p->d.k2; }
-    switch (which) {
-      case 0: case 1: case 2: *numel = s.C; break;
-      case 3: *numel = t1 * Cin * nh; break;
-      case 4: *numel = t2 * nh * nh; break;
-      case 5: *numel = t1 * Cout * nh; break;
-      default: *numel = nh; break;
-    }
+    *numel = p->numel[index];
+  });
+}
+
+int inb_glow_flat_layout(const inb_plan* p, long long* offsets, long long* total) {
+  return guarded([&] {
+    INB_CHECK(p != nullptr, "null plan");
+    if (offsets)
+      for (size_t i = 0; i < p->flat_off.size(); ++i) offsets[i] = p->flat_off[i];
+    if (total) *total = p->flat_total;
   });
 }
 
@@ -754,6 +815,58 @@ int inb_glow_zdims(const inb_plan* p, int batch, int scale, int* dims5) {
   dims5[n++] = s.g.H;
   dims5[n++] = s.g.W;
   return n;
+}
+
+// ---------------------------------------------------------------- data-parallel plane
+int inb_comm_unique_id(char* id128) {
+  return guarded([&] {
+    INB_CHECK(id128 != nullptr, "null id buffer");
+    dp_unique_id(id128);
+  });
+}
+int inb_comm_create(int nranks, int rank, const char* id128, inb_comm** out) {
+  return guarded([&] {
+    INB_CHECK(out && id128, "null argument");
+    *out = static_cast<inb_comm*>(dp_create(nranks, rank, id128));
+  });
+}
+int inb_comm_wrap(void* nccl_comm, inb_comm** out) {
+  return guarded([&] {
+    INB_CHECK(out != nullptr, "null output");
+    *out = static_cast<inb_comm*>(dp_wrap(nccl_comm));
+  });
+}
+int inb_comm_destroy(inb_comm* comm) {
+  return guarded([&] { dp_destroy(comm); });
+}
+int inb_comm_info(const inb_comm* comm, int* nranks, int* rank, long long* allreduce_calls, long long* allreduce_bytes) {
+  return guarded([&] {
+    INB_CHECK(comm != nullptr, "null communicator");
+    if (nranks) *nranks = comm->nranks;
+    if (rank) *rank = comm->rank;
+    if (allreduce_calls) *allreduce_calls = comm->calls;
+    if (allreduce_bytes) *allreduce_bytes = comm->bytes;
+  });
+}
+int inb_glow_plan_set_comm(inb_plan* p, inb_comm* comm) {
+  return guarded([&] {
+    INB_CHECK(p != nullptr, "null plan");
+    p->dp = comm;
+  });
+}
+int inb_allreduce_grads(inb_plan* p, float* const* grads, inb_comm* comm, void* stream) {
+  return guarded([&] {
+    INB_CHECK(p && grads && comm, "null argument");
+    dp_allreduce_avg_bucket(comm, grads, p->numel.data(), 0, (int)p->numel.size(), table_max_gap(p, grads),
+                            (cudaStream_t)stream);
+  });
+}
+int inb_broadcast_params(inb_plan* p, float* const* params, inb_comm* comm, int root, void* stream) {
+  return guarded([&] {
+    INB_CHECK(p && params && comm, "null argument");
+    dp_broadcast_f32(comm, params, p->numel.data(), (int)p->numel.size(), table_max_gap(p, params), root,
+                     (cudaStream_t)stream);
+  });
 }
 
 int inb_glow_forward(inb_plan* p, int batch, const float* X, float* const* params, float* Z, float* logdet,
@@ -1395,7 +1508,7 @@ int inb_hint_plan_create(const inb_hint_desc* d, inb_hint_plan** out) {
     INB_CHECK((d->k1 == 1 || d->k1 == 3) && (d->k2 == 1 || d->k2 == 3),
               "supported ResidualBlock kernel sizes are 1 and 3 (got k1=%d k2=%d)", d->k1, d->k2);
     INB_CHECK(d->p1 == (d->k1 - 1) / 2 && d->p2 == (d->k2 - 1) / 2, "only 'same' padding is supported");
-    INB_CHECK(d->precision >= 0 && d->precision <= 2, "unknown precision mode %d", d->precision);
+    INB_CHECK(d->precision >= 0 && d->precision <= 3, "unknown precision mode %d", d->precision);
     INB_CHECK(d->sig_high > d->sig_low, "sigmoid high must exceed low");
     INB_CHECK(d->squeeze_type == 0 || d->squeeze_type == 1, "squeeze_type must be 0 (wavelet) or 1 (Haar)");
     std::unique_ptr<inb_hint_plan> p(new inb_hint_plan());

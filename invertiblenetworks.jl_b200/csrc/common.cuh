@@ -129,16 +129,21 @@ struct SideLane {
   }
 };
 
+struct DpComm;  // dp.cuh
 struct Ctx {
   cudaStream_t st;
   Arena* ar;
   int prec;  // INB_PREC_*
   SideLane* lane = nullptr;
+  DpComm* dp = nullptr;   // data-parallel communicator attached to the plan (global-batch ActNorm statistics)
   bool wg_defer = false;  // weight gradients of this flow step may leave the main stream (SideLane::wparity)
   bool dry() const { return ar->dry; }
 };
 
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+// INB_PREC_*: number of products per contraction term (3-term split or single pass) and the operand format
+inline int prec_terms(int prec) { return (prec == 1 || prec == 3) ? 3 : 1; }
+inline bool prec_f16(int prec) { return prec == 3; }
 
 // ---------------------------------------------------------------- launch accounting / profiling
 // Every op brackets its kernel launches with a Prof scope: the launch counter is always kept

@@ -200,7 +200,10 @@ constexpr int kI2cRow = 144;  // bytes per tile row: 16-byte chunks of consecuti
 __global__ void __launch_bounds__(kI2cThreads)
 k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float* __restrict__ in1,
             long long in1_bs, int C, int T, int ksz, int W, int H, int D, long long px, long long M, int kp,
-            int ones_col, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+            int ones_col, int f16, const uint32_t* __restrict__ smax, __nv_bfloat16* __restrict__ hi,
+            __nv_bfloat16* __restrict__ lo) {
+  float insc = 1.f;  // INB_PREC_FP16X3: a gradient operand is scaled by the power of two derived from its max|.|
+  if (smax) { float inv; f16_scale_from_max(__ldg(smax), insc, inv); }
   // per column: element offset relative to the pixel inside its source tensor, and (tap, which source)
   __shared__ int s_off[kI2cMaxK];
   __shared__ unsigned char s_tap[kI2cMaxK];  // tap index | 0x80 for the second source | 0xFF: padding column
@@ -254,18 +257,11 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
         const int off = s_off[k0 + j];
         const bool ok = tp != 0xFF && ((okmask >> (tp & 31)) & 1u);
         const float* src = (tp & 0x80) ? p1 : p0;
-        v[j] = ok ? __ldg(src + off) : ((k0 + j == ones_col) ? 1.f : 0.f);
+        v[j] = ok ? __ldg(src + off) * insc : ((k0 + j == ones_col) ? 1.f : 0.f);
       }
       uint32_t wh[8], wl[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float a = v[2 * q], bb = v[2 * q + 1];
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
-        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
-        wh[q] = hw;
-        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
-      }
+      for (int q = 0; q < 8; ++q) split2_rt(f16 != 0, v[2 * q], v[2 * q + 1], wh[q], wl[q]);
       const int o = lane * kI2cRow + g * 32;
       *reinterpret_cast<uint4*>(th + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
       *reinterpret_cast<uint4*>(th + o + 16) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
@@ -292,8 +288,10 @@ k_im2col_tc(const float* __restrict__ in0, long long in0_bs, int c0, const float
 template <int C>
 __global__ void __launch_bounds__(kI2cThreads)
 k_im2col9_tc(const float* __restrict__ in0, long long in0_bs, int W, int H, long long px, long long M, int ones_col,
-             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+             int f16, const uint32_t* __restrict__ smax, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   constexpr int KR = 9 * C, KP = (KR + 63) / 64 * 64;
+  float insc = 1.f;
+  if (smax) { float inv; f16_scale_from_max(__ldg(smax), insc, inv); }
   __shared__ __align__(16) unsigned char s_tile[kI2cThreads / 32][2][32 * kI2cRow];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long m0 = (long long)blockIdx.x * kI2cPix + wid * 32;  // first pixel of this warp
@@ -326,21 +324,14 @@ k_im2col9_tc(const float* __restrict__ in0, long long in0_bs, int W, int H, long
         const int k = kb + g * 16 + j;  // compile-time after unrolling
         if (k < KR) {
           const int tap = k / C, ch = k - tap * C;
-          v[j] = ok[tap] ? __ldg(p0 + (ch * ipx + doff[tap])) : 0.f;
+          v[j] = ok[tap] ? __ldg(p0 + (ch * ipx + doff[tap])) * insc : 0.f;
         } else {
           v[j] = (k == ones_col) ? 1.f : 0.f;
         }
       }
       uint32_t wh[8], wl[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float a = v[2 * q], bb = v[2 * q + 1];
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-        const uint32_t hw = *reinterpret_cast<uint32_t*>(&h2);
-        __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), bb - __uint_as_float(hw & 0xFFFF0000u));
-        wh[q] = hw;
-        wl[q] = *reinterpret_cast<uint32_t*>(&l2);
-      }
+      for (int q = 0; q < 8; ++q) split2_rt(f16 != 0, v[2 * q], v[2 * q + 1], wh[q], wl[q]);
       const int o = lane * kI2cRow + g * 32;
       *reinterpret_cast<uint4*>(th + o) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
       *reinterpret_cast<uint4*>(th + o + 16) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
@@ -361,8 +352,10 @@ k_im2col9_tc(const float* __restrict__ in0, long long in0_bs, int W, int H, long
   }
 }
 template <int C>
-static void launch_im2col9(Ctx& c, const Geo& g, long long M, const float* in0, long long in0_bs, int ones_col, Planes out) {
-  k_im2col9_tc<C><<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, g.W, g.H, g.px, M, ones_col, out.hi, out.lo);
+static void launch_im2col9(Ctx& c, const Geo& g, long long M, const float* in0, long long in0_bs, int ones_col,
+                           const uint32_t* smax, Planes out) {
+  k_im2col9_tc<C><<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, g.W, g.H, g.px, M, ones_col,
+                                                                     prec_f16(c.prec) ? 1 : 0, smax, out.hi, out.lo);
 }
 static bool im2col_fast_enabled() {
   static const bool on = [] { const char* e = getenv("INB_IM2COL_FAST"); return !(e && e[0] == '0'); }();
@@ -370,7 +363,7 @@ static bool im2col_fast_enabled() {
 }
 
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
-                  long long in1_bs, int C, int kp, int ones_col, Planes out) {
+                  long long in1_bs, int C, int kp, int ones_col, Planes out, const uint32_t* smax) {
   if (c.dry()) return;
   const long long M = g.px * B;
   const int T = k == 1 ? 1 : (g.nd == 3 ? 27 : 9);
@@ -380,15 +373,15 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
   if (k == 3 && g.nd == 2 && (in1 == nullptr || c0 >= C) && kp == (9 * C + 63) / 64 * 64 && im2col_fast_enabled()) {
     bool done = true;
     switch (C) {
-      case 2: launch_im2col9<2>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 4: launch_im2col9<4>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 6: launch_im2col9<6>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 8: launch_im2col9<8>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 12: launch_im2col9<12>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 16: launch_im2col9<16>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 24: launch_im2col9<24>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 32: launch_im2col9<32>(c, g, M, in0, in0_bs, ones_col, out); break;
-      case 48: launch_im2col9<48>(c, g, M, in0, in0_bs, ones_col, out); break;
+      case 2: launch_im2col9<2>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 4: launch_im2col9<4>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 6: launch_im2col9<6>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 8: launch_im2col9<8>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 12: launch_im2col9<12>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 16: launch_im2col9<16>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 24: launch_im2col9<24>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 32: launch_im2col9<32>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
+      case 48: launch_im2col9<48>(c, g, M, in0, in0_bs, ones_col, smax, out); break;
       default: done = false;
     }
     if (done) {
@@ -397,7 +390,38 @@ void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long lon
     }
   }
   k_im2col_tc<<<(unsigned)cdiv(M, kI2cPix), kI2cThreads, 0, c.st>>>(in0, in0_bs, c0, in1, in1_bs, C, T, k, g.W, g.H, g.D, g.px, M,
-                                                          kp, ones_col, out.hi, out.lo);
+                                                          kp, ones_col, prec_f16(c.prec) ? 1 : 0, smax, out.hi, out.lo);
+  INB_CUDA(cudaGetLastError());
+}
+
+// bits of max|x| over a (B, C, px) tensor (samples `bs` elements apart, `per` contiguous elements each); the bit
+// patterns of non-negative floats are ordered like the values, so one atomicMax per warp finishes the reduction
+template <int V>
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, long long bs, long long per, int B,
+                                                uint32_t* __restrict__ out) {
+  const long long nv = per / V, n = nv * B;
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / nv, r = i - b * nv;
+    if (V == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * bs) + r);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    } else {
+      m = fmaxf(m, fabsf(__ldg(x + b * bs + r)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+void op_absmax(Ctx& c, long long px, int B, int C, const float* x, long long bs, uint32_t* smax) {
+  if (c.dry()) return;
+  const long long per = (long long)C * px;
+  Prof pf(c, F_LAYOUT_TC, 1, 0, 4.0 * per * B);
+  const bool v4 = per % 4 == 0 && bs % 4 == 0 && ((uintptr_t)x & 15) == 0;
+  const unsigned grid = (unsigned)std::min<long long>(cdiv(per * B / (v4 ? 4 : 1), 256 * 4), 148 * 8);
+  if (v4) k_absmax<4><<<std::max(grid, 1u), 256, 0, c.st>>>(x, bs, per, B, smax);
+  else k_absmax<1><<<std::max(grid, 1u), 256, 0, c.st>>>(x, bs, per, B, smax);
   INB_CUDA(cudaGetLastError());
 }
 
@@ -461,7 +485,7 @@ void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out) {
   long long blocks = std::min<long long>(cdiv(M, 64), 148 * 4);
   long long rpb = cdiv(M, blocks);
   // single-pass bf16 keeps only the hi planes
-  k_colsum_tc<<<(unsigned)cdiv(M, rpb), threads, 0, c.st>>>((const uint32_t*)in.hi, c.prec == 1 ? (const uint32_t*)in.lo : nullptr, M, C2, rpb, out);
+  k_colsum_tc<<<(unsigned)cdiv(M, rpb), threads, 0, c.st>>>((const uint32_t*)in.hi, prec_terms(c.prec) == 3 ? (const uint32_t*)in.lo : nullptr, M, C2, rpb, out);
   INB_CUDA(cudaGetLastError());
 }
 

@@ -34,8 +34,12 @@ void op_pack_w_tc(Ctx& c, int mode, int d0, int d1, int T, const float* w, int n
                   int add_identity = 0);
 // im2col rows for the fused chain's first GEMM and for the weight gradients (conv_tc.cu: k_im2col_tc):
 // out [M][kp] with kp = chain_kpad(T*C); `ones_col` (>= 0) is a column of ones
+// smax (INB_PREC_FP16X3, gradient operands): device word holding the bits of max|in|; the rows are scaled by the
+// power of two f16_scale_from_max derives from it
 void op_im2col_tc(Ctx& c, const Geo& g, int B, int k, const float* in0, long long in0_bs, int c0, const float* in1,
-                  long long in1_bs, int C, int kp, int ones_col, Planes out);
+                  long long in1_bs, int C, int kp, int ones_col, Planes out, const uint32_t* smax = nullptr);
+// bits of max|x| over a (B, C, px) tensor -> *smax (atomicMax; the caller zeroes it)
+void op_absmax(Ctx& c, long long px, int B, int C, const float* x, long long bs, uint32_t* smax);
 // per-channel sum over rows of planes [M][C] -> out[C] (bias gradients)
 void op_colsum_tc(Ctx& c, long long M, int C, Planes in, float* out);
 
@@ -84,6 +88,7 @@ struct Wgrad2TcSpec {
   int C, T;
   float* dw;
   float* db;
+  const uint32_t* smax = nullptr;  // INB_PREC_FP16X3: one operand carries the gradient scale; the reduction divides by it
 };
 void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
 void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n);  // one reduction launch for up to three gradients
@@ -108,6 +113,7 @@ struct ChainSpec {
   float* out0; long long out0_bs; int n0;
   float* out1; long long out1_bs; int out1_accum;
   const float* add; long long add_bs; int add_n;
+  const uint32_t* smax = nullptr;  // INB_PREC_FP16X3 backward pass: the scale of `in` (col2im divides by it)
 };
 int chain_n3pad(int taps, int Cn);
 int chain_kpad(int taps, int C, int extra);  // im2col width: taps*C (+ extra columns) rounded up to 64

@@ -51,6 +51,8 @@ struct ChainArgs {
   int pstag_bytes;        // k_rb_chain2: size of the P staging area
   int npiece, n3piece;    // k_rb_chain2: GEMM3 runs in npiece passes of n3piece (<= 256) columns through the same TMEM region
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
+  float wsinv;            // accumulators of GEMM1 / GEMM2 are multiplied by this before the epilogue's bias / mask:
+                          // 1 / kF16WScale when the weights were packed scaled (INB_PREC_FP16X3), else 1 (exact)
   int store;              // write both hidden tensors to HBM
   const float *bias1, *bias2;
   // relu-grad masks as bit planes [M][nh/32] uint32 in channel order: bit (ch & 31) of word (ch >> 5) of a row
@@ -80,9 +82,9 @@ __device__ __forceinline__ constexpr int chain_bit_base(int g) { return ((g & 1)
 // 8 accumulator columns -> packed bf16 hi / lo words.  MODE 0: + bias, ReLU; when BITS the signs of the 8
 // pre-activations are merged into `bits` (the _relugrad mask of activation_functions.jl:84, kept as a bit plane).
 // MODE 1: columns whose bit in `mbits` is set are zeroed.  g = index of the 8-column group inside the mask word.
-template <int MODE, int NT, bool BITS>
+template <int MODE, int NT, bool BITS, bool F16 = false>
 __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, uint32_t mbits, int g, uint32_t& bits,
-                                            uint4& oh, uint4& ol) {
+                                            uint4& oh, uint4& ol, float wsinv = 1.f) {
   float bias[8];
   if (MODE == 0) {
     const float4 b0 = *reinterpret_cast<const float4*>(sb), b1 = *reinterpret_cast<const float4*>(sb + 4);
@@ -96,8 +98,8 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
   for (int j = 0; j < 4; ++j) {
     float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
     if (MODE == 0) {
-      a += bias[2 * j];
-      b += bias[2 * j + 1];
+      a = fmaf(a, wsinv, bias[2 * j]);      // wsinv == 1: the same single rounding as a + bias
+      b = fmaf(b, wsinv, bias[2 * j + 1]);
       if (BITS) {
         b8 = __funnelshift_l(__float_as_uint(a), b8, 1);  // (b8 << 1) | sign(a)
         b8 = __funnelshift_l(__float_as_uint(b), b8, 1);
@@ -105,19 +107,18 @@ __device__ __forceinline__ void chain_pack8(const uint32_t* r, const float* sb, 
       a = fmaxf(a, 0.f);
       b = fmaxf(b, 0.f);
     } else {
+      a *= wsinv;
+      b *= wsinv;
       if ((mbits >> (base + 7 - 2 * j)) & 1u) a = 0.f;
       if ((mbits >> (base + 6 - 2 * j)) & 1u) b = 0.f;
     }
-    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-    uint32_t h = *reinterpret_cast<uint32_t*>(&h2);
     if (NT == 3) {
-      const float ra = a - __uint_as_float(h << 16), rb = b - __uint_as_float(h & 0xFFFF0000u);
-      __nv_bfloat162 l2 = __floats2bfloat162_rn(ra, rb);
-      pl[j] = *reinterpret_cast<uint32_t*>(&l2);
+      split2<F16>(a, b, ph[j], pl[j]);
     } else {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      ph[j] = *reinterpret_cast<uint32_t*>(&h2);
       pl[j] = 0;
     }
-    ph[j] = h;
   }
   if (MODE == 0 && BITS) bits |= b8 << base;
   oh = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -937,7 +938,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-template <int NT, bool TRACE>
+template <int NT, bool TRACE, bool F16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChain2Threads, 1)
 k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
@@ -1072,8 +1073,8 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA, both tiles of the pair)
     if (leader && elect_one()) {
-      const uint32_t idesc_12 = make_idesc_bf16(256, nhh, 0, 0);   // GEMM1 / GEMM2 run one column half at a time
-      const uint32_t idesc_3 = make_idesc_bf16(256, a.n3piece, 0, 0);
+      const uint32_t idesc_12 = make_idesc_16(256, nhh, 0, 0, F16);   // GEMM1 / GEMM2 run one column half at a time
+      const uint32_t idesc_3 = make_idesc_16(256, a.n3piece, 0, 0, F16);
       const uint32_t dhi = (uint32_t)(make_smem_desc(0, 0, 1024, LAYOUT_SW128) >> 32);
       uint32_t it = 0, tl = 0;
       long long twait = 0;
@@ -1310,10 +1311,10 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           for (int g = 0; g < 2; ++g) {
             uint4 oh, ol;
             if (a.mode == 0) {
-              if (a.store) chain_pack8<0, NT, true>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
-              else chain_pack8<0, NT, false>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol);
+              if (a.store) chain_pack8<0, NT, true, F16>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol, a.wsinv);
+              else chain_pack8<0, NT, false, F16>(r + 8 * g, sb + 64 * c + 8 * g, 0u, g, bits, oh, ol, a.wsinv);
             } else {
-              chain_pack8<1, NT, false>(r + 8 * g, sb, mm, g, bits, oh, ol);
+              chain_pack8<1, NT, false, F16>(r + 8 * g, sb, mm, g, bits, oh, ol, a.wsinv);
             }
             wh[4 * g] = oh.x; wh[4 * g + 1] = oh.y; wh[4 * g + 2] = oh.z; wh[4 * g + 3] = oh.w;
             wl[4 * g] = ol.x; wl[4 * g + 1] = ol.y; wl[4 * g + 2] = ol.z; wl[4 * g + 3] = ol.w;
@@ -1497,7 +1498,16 @@ struct Col2imArgs {
   float* out0; long long out0_bs; int n0;
   float* out1; long long out1_bs; int out1_accum;
   const float* add; long long add_bs; int add_n;
+  // INB_PREC_FP16X3: P carries the weight scale of the last contraction (oscale = 1 / kF16WScale) and, in the backward
+  // pass, the gradient scale derived from *smax; both are powers of two, removed here before the passthrough add
+  float oscale;
+  const uint32_t* smax;
 };
+__device__ __forceinline__ float col2im_scale(const Col2imArgs& a) {
+  float s = a.oscale;
+  if (a.smax) { float sc, inv; f16_scale_from_max(__ldg(a.smax), sc, inv); s *= inv; }
+  return s;
+}
 // thread = pixel: every tap (or tap row) contributes V-wide vectors of the pixel's P row, the sums stay in registers
 // (16 channels at a time) and each channel is stored with the warp's 32 consecutive pixels (coalesced both ways, no
 // shared memory; the 144-byte row stride of the loads is absorbed by L1, every byte of a row is used)
@@ -1510,6 +1520,7 @@ __global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
   const int x = (int)(t % a.W); t /= a.W;
   const int y = (int)(t % a.H); t /= a.H;
   const int z = (int)t;
+  const float osc = col2im_scale(a);
   for (int c0 = 0; c0 < a.Cn; c0 += 16) {
     float acc[16];
 #pragma unroll
@@ -1540,7 +1551,7 @@ __global__ void __launch_bounds__(128) k_col2im(const Col2imArgs a) {
     for (int j = 0; j < 16; ++j) {
       const int n = c0 + j;
       if (n < a.Cn) {
-        float v = acc[j];
+        float v = acc[j] * osc;
         if (a.add && n < a.add_n) v += a.add[b * a.add_bs + (long long)n * a.px + pix];
         if (n < a.n0) {
           a.out0[b * a.out0_bs + (long long)n * a.px + pix] = v;
@@ -1593,7 +1604,8 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
         a.P + (m + dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.cstride + 4 * g));
     acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
   }
-  const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+  const float osc = col2im_scale(a);
+  const float v4[4] = {acc.x * osc, acc.y * osc, acc.z * osc, acc.w * osc};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int n = 4 * g + j;
@@ -1616,6 +1628,7 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
 //   w3 [n3pad][nh]  tap-expanded rows of the \nabla conv_data contraction:  row tap*Cn + n  <-  wc[c][n][tap]
 // (wa = W1, wc = W3 in the forward pass; wa = W3, wc = W1 in the backward pass; reference layout w[d0][d1][T])
 struct PackChainArgs {
+  int f16;       // INB_PREC_FP16X3: IEEE-half planes of kF16WScale * w
   int nh, T, C1, kp, Cn, n3pad, w2_data;
   const float *wa, *wb, *wc;
   __nv_bfloat16 *w1h, *w1l, *w2h, *w2l, *w3h, *w3l;
@@ -1650,14 +1663,22 @@ __global__ void k_pack_chain_tc(const PackChainArgs a) {
       }
       dh = a.w3h; dl = a.w3l;
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    dh[o] = h;
-    dl[o] = l;
+    if (a.f16) {
+      uint32_t hw, lw;
+      split2<true>(v * kF16WScale, 0.f, hw, lw);
+      reinterpret_cast<unsigned short*>(dh)[o] = (unsigned short)(hw & 0xFFFFu);
+      reinterpret_cast<unsigned short*>(dl)[o] = (unsigned short)(lw & 0xFFFFu);
+    } else {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      dh[o] = h;
+      dl[o] = l;
+    }
   }
 }
 constexpr int kPackMulti = 24;
 struct PackMultiArgs {
+  int f16;
   int nh, T, C1, kp, Cn, n3pad, w2_data, n, blocks_per_item;
   const float* wa[kPackMulti];
   const float* wb[kPackMulti];
@@ -1695,10 +1716,17 @@ __global__ void k_pack_chain_multi(const __grid_constant__ PackMultiArgs a) {
       }
       which = 4;
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    a.dst[item][which][o] = h;
-    a.dst[item][which + 1][o] = l;
+    if (a.f16) {
+      uint32_t hw, lw;
+      split2<true>(v * kF16WScale, 0.f, hw, lw);
+      reinterpret_cast<unsigned short*>(a.dst[item][which])[o] = (unsigned short)(hw & 0xFFFFu);
+      reinterpret_cast<unsigned short*>(a.dst[item][which + 1])[o] = (unsigned short)(lw & 0xFFFFu);
+    } else {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      a.dst[item][which][o] = h;
+      a.dst[item][which + 1][o] = l;
+    }
   }
 }
 void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int Cn, int n3pad, const PackChainItem* items,
@@ -1707,6 +1735,7 @@ void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int
   const long long per = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
   for (int i0 = 0; i0 < n; i0 += kPackMulti) {
     PackMultiArgs a{};
+    a.f16 = prec_f16(c.prec) ? 1 : 0;
     a.nh = nh; a.T = T; a.C1 = C1; a.kp = kp; a.Cn = Cn; a.n3pad = n3pad; a.w2_data = w2_data;
     a.n = std::min(kPackMulti, n - i0);
     a.blocks_per_item = (int)std::min<long long>(cdiv(per, 256), 64);
@@ -1724,7 +1753,7 @@ void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int
 void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
                       int n3pad, const float* wc, Planes w1, Planes w2, Planes w3) {
   if (c.dry()) return;
-  PackChainArgs a{nh, T, C1, kp, Cn, n3pad, w2_data, wa, wb, wc, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo};
+  PackChainArgs a{prec_f16(c.prec) ? 1 : 0, nh, T, C1, kp, Cn, n3pad, w2_data, wa, wb, wc, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo};
   const long long n = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
   Prof pf(c, F_PACK, 1, 0, 8.0 * n);
   k_pack_chain_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(a);
@@ -1760,9 +1789,11 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   const int taps = s.k1 == 1 ? 1 : (s.g.nd == 3 ? 27 : 9);
   INB_CHECK(s.in.pitch % 64 == 0 && s.w1.pitch == s.in.pitch, "fused ResidualBlock chain: the im2col width must be a multiple of 64");
   if (c.dry()) return;
-  const int NT = (c.prec == 1) ? 3 : 1;
+  const int NT = prec_terms(c.prec);
+  const bool f16 = prec_f16(c.prec);
   const int NP = NT == 1 ? 1 : 2;
   ChainArgs a{};
+  a.wsinv = f16 ? 1.f / kF16WScale : 1.f;
   a.W = s.g.W; a.H = s.g.H; a.D = s.g.D;
   a.M = s.g.px * s.B;
   a.ntiles = (int)cdiv(a.M, 128);
@@ -1795,6 +1826,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
   }();
   const bool pair = (a.n3pad <= 256 || (a.n3pad <= 512 && a.n3pad % 32 == 0)) && force == 0;
+  INB_CHECK(pair || !f16, "precision fp16x3 runs on the CTA-pair chain kernel only (use bf16x3 for this shape)");
   a.npiece = a.n3pad <= 256 ? 1 : 2;
   a.n3piece = a.n3pad / a.npiece;
   static const bool no_qsum = [] { const char* e = getenv("INB_CHAIN_QSUM"); return e && e[0] == '0'; }();
@@ -1835,12 +1867,12 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   {
     Prof pf(c, F_CONV_TC, 1, flops, 0);
     if (pair) {
-      auto kern = a.trace ? ((NT == 3) ? k_rb_chain2<3, true> : k_rb_chain2<1, true>)
-                          : ((NT == 3) ? k_rb_chain2<3, false> : k_rb_chain2<1, false>);
+      auto kern = a.trace ? (f16 ? k_rb_chain2<3, true, true> : ((NT == 3) ? k_rb_chain2<3, true> : k_rb_chain2<1, true>))
+                          : (f16 ? k_rb_chain2<3, false, true> : ((NT == 3) ? k_rb_chain2<3, false> : k_rb_chain2<1, false>));
       INB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       // resident CTA pairs: one CTA per SM, pairs are placed inside a GPC (the query accounts for odd GPCs)
-      static int max_pairs[4] = {0, 0, 0, 0};
-      int& mpairs = max_pairs[(NT == 3) + 2 * (a.trace != nullptr)];
+      static int max_pairs[6] = {0, 0, 0, 0, 0, 0};
+      int& mpairs = max_pairs[(NT == 3) + (f16 ? 1 : 0) + 3 * (a.trace != nullptr)];
       if (mpairs == 0) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(148);
@@ -1886,6 +1918,8 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     ca.out0 = s.out0; ca.out0_bs = s.out0_bs; ca.n0 = s.n0;
     ca.out1 = s.out1; ca.out1_bs = s.out1_bs; ca.out1_accum = s.out1_accum;
     ca.add = s.add; ca.add_bs = s.add_bs; ca.add_n = s.add_n;
+    ca.oscale = f16 ? 1.f / kF16WScale : 1.f;
+    ca.smax = f16 ? s.smax : nullptr;
     Prof pf(c, F_COL2IM, 1, 0, (4.0 * ca.n3pad + 4.0 * s.Cn) * a.M);
     const unsigned nb = (unsigned)cdiv(a.M, 128);
     const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;

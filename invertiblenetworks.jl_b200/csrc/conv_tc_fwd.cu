@@ -309,7 +309,7 @@ void op_conv_tc(Ctx& c, const ConvTcSpec& s) {
   INB_CHECK(tb.ok, "spatial size %dx%dx%d cannot be tiled for the tensor-core path; use precision fp32", s.g.W,
             s.g.H, s.g.D);
   if (c.dry()) return;
-  const int NT = (c.prec == 1) ? 3 : 1;
+  const int NT = prec_terms(c.prec);
   const int NP = NT == 1 ? 1 : 2;
   ConvTcArgs a{};
   a.taps = s.k == 1 ? 1 : (s.g.nd == 3 ? 27 : 9);

@@ -35,6 +35,7 @@ struct Wgrad2Args {
   int stages;
   uint32_t stage_bytes, p_plane, q_plane;  // per plane: P tile, Q tile (of the widest group)
   float* dbpart;    // [gridDim.x][np] partial bias sums, nullable
+  int f16;          // operand planes are IEEE halves (INB_PREC_FP16X3)
 };
 
 template <int NT>
@@ -99,7 +100,7 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, nqg, 1, 1);
+      const uint32_t idesc = make_idesc_16(128, nqg, 1, 1, a.f16 != 0);
       // MN-major SWIZZLE_128B: LBO = byte distance between 64-element atoms along M / N, SBO = 8 pixel rows
       const uint32_t dhi = (uint32_t)(make_smem_desc(0, ATOM, 1024, LAYOUT_SW128) >> 32);
       const uint32_t dlo_lbo = ((ATOM >> 4) & 0x3FFF) << 16;
@@ -139,12 +140,12 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
         for (int px = 0; px < kWgPB; ++px) {
           const uint32_t off = px * 128 + ((((uint32_t)lane >> 2) ^ (px & 7)) << 4) + (lane & 3) * 4;
           const uint32_t h = *reinterpret_cast<const uint32_t*>(at + off);
-          s0 += bf16lo_to_f(h);
-          s1 += bf16hi_to_f(h);
+          s0 += half_word_lo_to_f(a.f16 != 0, h);
+          s1 += half_word_hi_to_f(a.f16 != 0, h);
           if (NT == 3) {
             const uint32_t l = *reinterpret_cast<const uint32_t*>(at + a.p_plane + off);
-            s0 += bf16lo_to_f(l);
-            s1 += bf16hi_to_f(l);
+            s0 += half_word_lo_to_f(a.f16 != 0, l);
+            s1 += half_word_hi_to_f(a.f16 != 0, l);
           }
         }
         __syncwarp();
@@ -201,6 +202,7 @@ struct WgradReduceDesc {
   float* dw;
   const float* dbpart;
   float* db;
+  const uint32_t* smax;  // INB_PREC_FP16X3: the sums carry the gradient scale derived from *smax
 };
 struct WgradReduceArgs {
   WgradReduceDesc d[3];
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
   const int ncta = q.ncta, np = q.np, pitch = q.pitch, C = q.C, T = q.T;
   const int ncol = T * C;
   const long long total = (long long)np * ncol, outs = total + (dbpart ? np : 0);
+  float osc = 1.f;
+  if (q.smax) { float sc; f16_scale_from_max(__ldg(q.smax), sc, osc); }
   const int sub = threadIdx.x >> 6;  // which quarter of the partials (a warp works on 32 consecutive outputs)
   const int ol = threadIdx.x & 63;
   __shared__ float sm[4][64];
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
     sm[sub][ol] = s0 + s1;
     __syncthreads();
     if (sub == 0 && i < outs) {
-      const float s = (sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol]);
+      const float s = ((sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol])) * osc;
       if (i >= total) {
         q.db[i - total] = s;
       } else {
@@ -259,9 +263,10 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   INB_CHECK(s.np == 128 || s.np == 256, "tensor-core wgrad: np = %d must be 128 or 256", s.np);
   INB_CHECK(s.Q.pitch % 64 == 0 && s.P.pitch == s.np, "tensor-core wgrad: operand pitches must be multiples of 64");
   INB_CHECK(s.T * s.C <= s.Q.pitch, "tensor-core wgrad: Q has %d columns, need %d", s.Q.pitch, s.T * s.C);
-  const int NT = (c.prec == 1) ? 3 : 1;
+  const int NT = prec_terms(c.prec);
   const int NP = NT == 1 ? 1 : 2;
   Wgrad2Args a{};
+  a.f16 = prec_f16(c.prec) ? 1 : 0;
   a.M = s.M;
   a.nblocks = (int)cdiv(s.M, kWgPB);
   a.np = s.np;
@@ -305,7 +310,7 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
     k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   }
   INB_CUDA(cudaGetLastError());
-  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, s.dw, a.dbpart, s.db};
+  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, s.dw, a.dbpart, s.db, prec_f16(c.prec) ? s.smax : nullptr};
   return (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
 }
 

@@ -5,6 +5,7 @@
 // pixels and all C channels of them in registers: every global access of a warp is a contiguous
 // 128*V-byte run per channel (coalesced, vectorised), each element is read once and written once.
 #include "ops.cuh"
+#include "dp.cuh"
 #include <algorithm>
 
 namespace inb {
@@ -310,7 +311,15 @@ void op_actnorm_init(Ctx& c, long long px, int B, int C, View x, float* s, float
     double n = (double)px * B;
     dim3 g = stat_grid(px * B, C);
     k_chan_stat<0><<<g, 256, 0, c.st>>>(x.p, x.bs, px, B, nullptr, 0.0, sum);
+    if (c.dp && c.dp->nranks > 1) {
+      // data parallel: the statistics of the GLOBAL batch (invertible_layer_actnorm.jl:67-72 on the concatenated
+      // shards; equal shards): sum over the ranks of the per-shard sums, then of the squared deviations from the
+      // global mean - the same two-pass mean / unbiased variance as on one device
+      dp_allreduce_sum_f64(c.dp, sum, C, c.st);
+      n *= c.dp->nranks;
+    }
     k_chan_stat<1><<<g, 256, 0, c.st>>>(x.p, x.bs, px, B, sum, 1.0 / n, ss);
+    if (c.dp && c.dp->nranks > 1) dp_allreduce_sum_f64(c.dp, ss, C, c.st);
     k_actnorm_init_finish<<<(C + 127) / 128, 128, 0, c.st>>>(sum, ss, n, C, s, b);
     INB_CUDA(cudaGetLastError());
   }

@@ -141,7 +141,10 @@ static void rb_backward_fp32(Ctx& c, const RBShape& s, const float* dY3, View x2
 // ---------------------------------------------------------------- ResidualBlock, tcgen05 path
 static int pad16(int n) { return (n + 15) / 16 * 16; }
 
-static void tc_check(const RBShape& s) {
+static bool rb_chain_ok(const RBShape& s);
+static void tc_check(const RBShape& s, int prec = 1) {
+  INB_CHECK(!prec_f16(prec) || rb_chain_ok(s),
+            "precision fp16x3 needs the fused ResidualBlock chain (k2 = 1, n_hidden in {128, 256}); use bf16x3 or fp32");
   INB_CHECK(s.nh % 128 == 0 && s.nh <= 256,
             "the tensor-core path needs n_hidden in {128, 256} (got %d); use precision fp32", s.nh);
   INB_CHECK(pad16(s.Cin()) <= 256 && pad16(s.Cout) <= 256, "the tensor-core path supports up to 256 channels");
@@ -191,7 +194,7 @@ static ConvTcSpec tc_base(const RBShape& s) {
 }
 
 static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
-  tc_check(s);
+  tc_check(s, c.prec);
   const long long px = s.g.px, M = px * s.B;
   const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2();
   const int cin_pad = pad16(Cin), cout_pad = pad16(s.Cout);
@@ -262,7 +265,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
 static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
                            RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs,
                            View dcond) {
-  tc_check(s);
+  tc_check(s, c.prec);
   const long long px = s.g.px, M = px * s.B;
   const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2(), Cout = s.Cout;
   const int cin_pad = pad16(Cin), cout_pad = pad16(Cout);
@@ -281,7 +284,15 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
       W3c = planes_new(c, nh, kp); W2d = planes_new(c, nh, nh); W1e = planes_new(c, n3pad, nh);
     }
     Planes dcol = planes_new(c, M, kp);
-    op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol);
+    // INB_PREC_FP16X3: every tensor of this pass is linear in dY3, so ONE power-of-two scale (from max|dY3|, found on
+    // the device) keeps the half-precision planes in their normal range; col2im and the gradient reduction divide by it
+    uint32_t* smax = nullptr;
+    if (prec_f16(c.prec)) {
+      smax = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes(256));
+      op_zero(c, smax, 4);
+      op_absmax(c, px, s.B, Cout, dY3, (long long)Cout * px, smax);
+    }
+    op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol, smax);
     // conv(dY3, W3) :151 | \nabla conv_data(., W2) + I (the '+ dY2' of :155) | \nabla conv_data(., W1) tap-expanded :162
     if (!p.pre[1]) op_pack_chain_tc(c, nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
     ChainSpec cs{};
@@ -293,11 +304,12 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;
     cs.out1 = dcond.p; cs.out1_bs = dcond.bs; cs.out1_accum = 1;
     cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
+    cs.smax = smax;
     op_rb_chain(c, cs);
     const Wgrad2TcSpec wg[3] = {
-        Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr},   // :152
-        Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2},           // :156-157
-        Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1}};     // :163-164
+        Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr, smax},   // :152
+        Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2, smax},           // :156-157
+        Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1, smax}};     // :163-164
     op_wgrad2_tc_multi(c, wg, 3);
     c.ar->release(m);
     return;

@@ -201,6 +201,79 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   return d;
 }
 
+// kind::f16 with IEEE half operands (a_format = b_format = F16 = 0), same rate as bf16: the x3 split then carries
+// 2 x 11 significant bits per operand instead of 2 x 8 (INB_PREC_FP16X3)
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major,
+                                                           uint32_t b_mn_major, bool f16) {
+  uint32_t d = make_idesc_bf16(M, N, a_mn_major, b_mn_major);
+  if (f16) d &= ~((7u << 7) | (7u << 10));
+  return d;
+}
+
+// ---------------------------------------------------------------- fp16 split (INB_PREC_FP16X3)
+// v = hi + lo with hi = RN_f16(v), lo = RN_f16(v - hi), both saturating at +-65504: the pair carries 22 significant
+// bits where lo is a normal half (|v| >= 2^-3) and an absolute error <= 2^-25 below (lo subnormal, quantum 2^-24).
+// Tensors whose magnitude is not O(1) are therefore pre-scaled by a power of two (weights: kF16WScale; gradients:
+// a per-call power of two derived from max|dY| on the device, see f16_scale_from_max).
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ float f16lo_to_f(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(packed));
+  return f;
+}
+__device__ __forceinline__ float f16hi_to_f(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(packed));
+  return f;
+}
+// packed (element a in the low half-word, b in the high one) hi and lo words of two values, in either operand format
+template <bool F16>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hw, uint32_t& lw) {
+  if (F16) {
+    hw = cvt_f16x2_sat(a, b);
+    lw = cvt_f16x2_sat(a - f16lo_to_f(hw), b - f16hi_to_f(hw));
+  } else {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hw = *reinterpret_cast<uint32_t*>(&h2);
+    __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hw << 16), b - __uint_as_float(hw & 0xFFFF0000u));
+    lw = *reinterpret_cast<uint32_t*>(&l2);
+  }
+}
+__device__ __forceinline__ void split2_rt(bool f16, float a, float b, uint32_t& hw, uint32_t& lw) {
+  if (f16) split2<true>(a, b, hw, lw);
+  else split2<false>(a, b, hw, lw);
+}
+__device__ __forceinline__ float half_word_lo_to_f(bool f16, uint32_t w) { return f16 ? f16lo_to_f(w) : __uint_as_float(w << 16); }
+__device__ __forceinline__ float half_word_hi_to_f(bool f16, uint32_t w) {
+  return f16 ? f16hi_to_f(w) : __uint_as_float(w & 0xFFFF0000u);
+}
+// weights are O(0.05) (glorot): scaled by 2^4 before the split so that their lo halves are normal numbers; the
+// epilogue that consumes the accumulator multiplies by 2^-4 (exact)
+constexpr float kF16WScale = 16.f;
+// Power-of-two scale s with max * s in [2^6, 2^7) from the bit pattern of max|x| (an fp32 >= 0; atomicMax on the bits);
+// returns 1 for max == 0 / denormal / non-finite.  inv = 1 / s, exact.
+__host__ __device__ __forceinline__ void f16_scale_from_max(uint32_t max_bits, float& s, float& inv) {
+  const int e = (int)((max_bits >> 23) & 0xFF);  // max in [2^(e-127), 2^(e-126))
+  if (e == 0 || e == 255) { s = 1.f; inv = 1.f; return; }
+  int se = 6 - (e - 127);                        // s = 2^se
+  if (se > 100) se = 100;
+  if (se < -100) se = -100;
+#ifdef __CUDA_ARCH__
+  s = __uint_as_float((uint32_t)(127 + se) << 23);
+  inv = __uint_as_float((uint32_t)(127 - se) << 23);
+#else
+  union { uint32_t u; float f; } a, b;
+  a.u = (uint32_t)(127 + se) << 23;
+  b.u = (uint32_t)(127 - se) << 23;
+  s = a.f;
+  inv = b.f;
+#endif
+}
+
 // ---------------------------------------------------------------- bf16 split
 // v = hi + lo (+ O(2^-17 |v|)): hi = RN_bf16(v), lo = RN_bf16(v - hi)
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

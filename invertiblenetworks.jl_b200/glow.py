@@ -451,6 +451,8 @@ class _GlowBase:
         import ctypes
         _l.call("inb_glow_plan_create", ctypes.byref(d), ctypes.byref(plan))
         self._plan, self._plan_key = plan, key + (B,)
+        if getattr(self, "_comm", None) is not None:  # dp.attach: the communicator follows the plan
+            _l.call("inb_glow_plan_set_comm", plan, self._comm._h)
         return plan
 
     def graph_stats(self):

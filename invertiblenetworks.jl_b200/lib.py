@@ -9,8 +9,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libinb200.so")
 
-PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_BF16X3, PREC_BF16, PREC_FP16X3 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16, "fp16x3": PREC_FP16X3}
 
 
 class GlowDesc(C.Structure):
@@ -59,6 +59,15 @@ SIGNATURES = {
     "inb_glow_forward": (I, [P, I, P, PP, P, P, I, P]),
     "inb_glow_inverse": (I, [P, I, P, PP, P, P]),
     "inb_glow_backward": (I, [P, I, P, P, PP, PP, P, P, P]),
+    "inb_glow_flat_layout": (I, [P, C.POINTER(LL), C.POINTER(LL)]),
+    "inb_comm_unique_id": (I, [C.c_char_p]),
+    "inb_comm_create": (I, [I, I, C.c_char_p, C.POINTER(P)]),
+    "inb_comm_wrap": (I, [P, C.POINTER(P)]),
+    "inb_comm_destroy": (I, [P]),
+    "inb_comm_info": (I, [P, C.POINTER(I), C.POINTER(I), C.POINTER(LL), C.POINTER(LL)]),
+    "inb_glow_plan_set_comm": (I, [P, P]),
+    "inb_allreduce_grads": (I, [P, PP, P, P]),
+    "inb_broadcast_params": (I, [P, PP, P, I, P]),
     "inb_cglow_forward": (I, [P, I, P, P, PP, P, P, P, I, P]),
     "inb_cglow_inverse": (I, [P, I, P, P, PP, P, P]),
     "inb_cglow_backward": (I, [P, I, P, P, P, PP, PP, P, P, P, P]),

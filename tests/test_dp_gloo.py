@@ -2,7 +2,6 @@
 single-process gradient of the global batch after ONE averaged all-reduce of the flat gradient buffer
 (SURVEY 8e).  The compute on each rank is the oracle (this is a test: the oracle is the checker's stand-in
 for the per-GPU library call); what is under test is invertiblenetworks.jl_b200/dp.py."""
-import importlib.util
 import os
 import socket
 import sys
@@ -16,10 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _load_dp():
-    spec = importlib.util.spec_from_file_location("inb_dp", os.path.join(ROOT, "invertiblenetworks.jl_b200", "dp.py"))
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
-    return m
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import inb200  # the shared library is only dlopen'ed by a compute call; none is made here
+    return inb200.dp
 
 
 def _free_port():
@@ -88,3 +87,27 @@ def test_shard_bounds():
     assert [dp.shard_bounds(64, r, 8) for r in (0, 7)] == [(0, 8), (56, 64)]
     with pytest.raises(ValueError):
         dp.shard_bounds(10, 0, 4)
+
+
+def test_flat_layout_of_the_library_is_the_mirrors_layout():
+    """inb_glow_flat_layout (the canonical layout a caller keeps its gradients in to get one collective per contiguous
+    range) equals the offsets the Python mirror gives its flat parameter / gradient buffers."""
+    import ctypes
+    import inb200
+    L = inb200.lib
+    for cond in (0, 2):
+        d = L.GlowDesc(2, 32, 32, 1, 3, cond, 16, 3, 2, 2, 1, 1, 3, 1, 1, 0, 0.0, 1.0, 0, 0)
+        plan = L.P()
+        L.call("inb_glow_plan_create", ctypes.byref(d), ctypes.byref(plan))
+        n = L.load().inb_glow_num_params(plan)
+        offs = (ctypes.c_longlong * n)()
+        tot = ctypes.c_longlong()
+        L.call("inb_glow_flat_layout", plan, offs, ctypes.byref(tot))
+        o, want = 0, []
+        for i in range(n):
+            want.append(o)
+            m = ctypes.c_longlong()
+            L.call("inb_glow_param_numel", plan, i, ctypes.byref(m))
+            o += (m.value + 63) // 64 * 64
+        assert list(offs) == want and tot.value == o
+        L.call("inb_glow_plan_destroy", plan)

@@ -223,63 +223,7 @@ def test_cuda_matches_golden():
         assert rel(p.grad, torch.from_numpy(gold[f"glow_g{i:03d}"])) < 10 * TOL_GRAD, i
 
 
-def test_full_size_cfg2_tensor_core_path_agrees_with_fp32_path():
-    """BASELINE configs[1] at full depth (L=3, K=16, n_hidden=256, 256x256x3), B=2: the tcgen05 bf16x3 path
-    (persistent CTA-pair kernels over thousands of tiles, all three scales) against the fp32 CUDA-core path of the
-    same library on identical parameters - two independent implementations, the second one oracle-checked at small
-    sizes.  Too big for the CPU oracle, hence this size-independent check; plus invertibility."""
-    torch.manual_seed(0)
-    G32 = inb200.NetworkGlow(3, 256, 3, 16, split_scales=True, precision="fp32", seed=1, device=DEV)
-    Gtc = inb200.NetworkGlow(3, 256, 3, 16, split_scales=True, precision="bf16x3", seed=1, device=DEV)
-    X = g(torch.rand(2, 3, 256, 256))
-    Z32, ld32 = G32.forward(X)   # data-dependent ActNorm init
-    inb200.set_params(Gtc, [p.data for p in G32.get_params()])
-    Ztc, ldtc = Gtc.forward(X)
-    assert rel(Ztc, Z32) < 1e-4
-    assert abs(ldtc.item() - ld32.item()) < 1e-4 * abs(ld32.item())
-    assert rel(Gtc.inverse(Ztc), X) < 1e-4
-    dZ = Z32 / 2
-    dX32, _ = G32.backward(dZ, Z32)
-    dXtc, Xr = Gtc.backward(dZ, Z32)
-    assert rel(Xr, X) < 1e-4
-    # The flow step that backward visits FIRST (scale 3, step K-1) sees identical inputs in both paths: its ten
-    # gradients must agree to float32-equivalent accuracy - this is the full-size check of the kernels themselves.
-    K, L = 16, 3
-    ps, qs = Gtc.get_params(), G32.get_params()
-    last = (L - 1) * K + (K - 1)
-    idx = [2 * last, 2 * last + 1] + [2 * L * K + 8 * last + k for k in range(8)]
-    for i in idx:
-        assert rel(ps[i].grad, qs[i].grad) < 1e-4, i
-    # Further down the two arithmetics recompute slightly different activations (8e-5 after 48 inversions) and a few
-    # ReLU units per million land on the other side of zero; each flip is an O(1) local change, so the difference of
-    # the gradients grows to ~1e-2 at the first flow step (measured: scripts/grad_agree.py, same with the older
-    # kernels; DESIGN.md section 8).  Bound it loosely here.
-    assert rel(dXtc, dX32) < 5e-2
-    worst = max(rel(p.grad, q.grad) for p, q in zip(ps, qs))
-    assert worst < 1e-1, worst
-
-
-def test_full_size_cfg5_3d_and_cfg3_conditional_properties():
-    """BASELINE configs[4] (3-D Glow on 64^3 x 1, L=2, K=2, n_hidden=32, B=2) and configs[2] (conditional Glow 64x64,
-    L=2, K=10, n_hidden=32, B=8) at full size: invertibility, finite outputs and gradients (test_glow.jl:46,
-    test_conditional_glow_network.jl:31-46)."""
-    torch.manual_seed(0)
-    G = inb200.NetworkGlow3D(1, 32, 2, 2, split_scales=True, device=DEV)
-    X = g(torch.rand(2, 1, 64, 64, 64))
-    Z, ld = G.forward(X)
-    assert torch.isfinite(Z).all() and torch.isfinite(ld)
-    assert rel(G.inverse(Z), X) < 1e-5
-    dX, Xr = G.backward(Z / 2, Z)
-    assert rel(Xr, X) < 1e-5 and torch.isfinite(dX).all()
-    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in G.get_params())
-
-    C = inb200.NetworkConditionalGlow(1, 1, 32, 2, 10, split_scales=True, device=DEV)
-    Xc, Cn = g(torch.rand(8, 1, 64, 64)), g(torch.rand(8, 1, 64, 64))
-    ZX, ZC, ldc = C.forward(Xc, Cn)
-    assert torch.isfinite(ZX).all() and torch.isfinite(ldc)
-    assert rel(C.inverse(ZX, ZC), Xc) < 1e-5
-    out = C.backward(ZX / 8, ZX, ZC)
-    assert rel(out[1], Xc) < 1e-5 and torch.isfinite(out[0]).all() and torch.isfinite(out[2]).all()
+# Full-size parity of cfg2 / cfg3 / cfg5 against the float64 oracle: tests/test_gpu_fullsize.py.
 
 
 def test_checkpoint_roundtrip_in_get_params_order(tmp_path):

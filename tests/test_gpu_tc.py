@@ -11,10 +11,10 @@ import inb200
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL_BF16 = 1.5e-1   # single-pass bf16 operands (8-bit mantissa), fp32 accumulate; ReLU-mask flips dominate the backward error
-TOLS = {"bf16x3": (TOL_OUT, TOL_GRAD), "bf16": (TOL_BF16, 2 * TOL_BF16)}
+TOLS = {"bf16x3": (TOL_OUT, TOL_GRAD), "fp16x3": (TOL_OUT, TOL_GRAD), "bf16": (TOL_BF16, 2 * TOL_BF16)}
 # a ReLU unit is "fragile" when its pre-activation is closer to zero than the arithmetic's own error
-FRAGILE = {"bf16x3": 1e-4, "bf16": 3e-2}
-INV_TOL = {"bf16x3": 1e-5, "bf16": 1e-2}  # bf16 rounding of the block input is discontinuous: ~1e-4 per layer
+FRAGILE = {"bf16x3": 1e-4, "fp16x3": 1e-5, "bf16": 3e-2}
+INV_TOL = {"bf16x3": 1e-5, "fp16x3": 1e-5, "bf16": 1e-2}  # bf16 rounding of the block input is discontinuous: ~1e-4 per layer
 
 
 def g(t):
@@ -33,12 +33,14 @@ RB_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("case", RB_CASES)
 def test_resblock_tc(case, prec):
     torch.manual_seed(4)
     tol_out, tol_grad = TOLS[prec]
     B, Cin, nh, Cout, sp, k1, k2 = case
+    if prec == "fp16x3" and k2 != 1:
+        pytest.skip("fp16x3 runs on the fused chain only (k2 = 1)")
     nd = len(sp)
     RB = inb200.ResidualBlock(Cin, nh, n_out=Cout, k1=k1, k2=k2, p1=(k1 - 1) // 2, p2=(k2 - 1) // 2, ndims=nd,
                               precision=prec, gen=torch.Generator().manual_seed(3), device=DEV)
@@ -59,7 +61,7 @@ def test_resblock_tc(case, prec):
         assert_grad_close(p.grad, q.grad, tol_grad, fr, name)
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
 @pytest.mark.parametrize("case", [(2, 12, 0, 128, (16, 16)), (2, 4, 4, 128, (16, 16)), (2, 8, 0, 128, (8, 8, 8))])
 def test_coupling_layer_tc(case, prec):
     torch.manual_seed(6)
@@ -94,15 +96,16 @@ def test_coupling_layer_tc(case, prec):
     (5, 6, 128, 12, (16, 16)),     # odd number of tiles: the last pair has an empty tile
     (2, 24, 256, 48, (32, 32)),    # scale-3 plan: forward on the single-CTA kernel, backward on pairs
 ])
-def test_resblock_tc_many_tiles_per_pair(case, monkeypatch):
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_resblock_tc_many_tiles_per_pair(case, prec, monkeypatch):
     """The persistent loop of the CTA-pair kernel (ring wrap, barrier parities, TMEM region swap, staging reuse)
     over many tiles per pair: the number of resident pairs is capped at 2, so a small input already walks 4-16
     tile pairs per cluster."""
     monkeypatch.setenv("INB_CHAIN_MAXPAIRS", "2")
-    test_resblock_tc(case + (3, 1), "bf16x3")
+    test_resblock_tc(case + (3, 1), prec)
 
 
-@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "bf16"])
 def test_glow_network_tc(prec):
     """cfg2's channel plan (3 -> 12/24/48) with n_hidden = 128 at 64x64, L = 3."""
     from test_gpu_networks import run_glow_parity
@@ -111,7 +114,30 @@ def test_glow_network_tc(prec):
                     fragile_thr=FRAGILE[prec], inv_tol=INV_TOL[prec])
 
 
+def test_fp16x3_gradient_scale_covers_tiny_and_huge_gradients():
+    """fp16x3 derives one power-of-two scale per ResidualBlock backward from max|dY| on the device: gradients of
+    magnitude 1e-9 or 1e+6 (far outside the range of an IEEE half) must come out as accurately as O(1) ones."""
+    torch.manual_seed(8)
+    B, Cin, nh, Cout, sp = 2, 6, 128, 12, (16, 16)
+    RB = inb200.ResidualBlock(Cin, nh, n_out=Cout, k1=3, k2=1, p1=1, p2=0, precision="fp16x3",
+                              gen=torch.Generator().manual_seed(3), device=DEV)
+    ws = [p.data.cpu().double() for p in RB.get_params()]
+    R64 = O.ResidualBlock(*ws, p1=1, p2=0)
+    X, dY = torch.randn(B, Cin, *sp), torch.randn(B, Cout, *sp)
+    for mag in (1e-9, 1.0, 1e6):
+        dX = RB.backward(g(dY * mag), g(X))
+        with FragileUnits(1e-5) as fr:
+            dX64 = R64.backward(dY.double() * mag, X.double())
+        assert_grad_close(dX, dX64, TOL_OUT, fr, f"dX at |dY| ~ {mag}")
+        for name, p, q in zip("W1 W2 W3 b1 b2".split(), RB.get_params(), R64.params()):
+            assert_grad_close(p.grad, q.grad, TOL_GRAD, fr, f"{name} at |dY| ~ {mag}")
+    assert torch.equal(RB.backward(g(dY * 0), g(X)).cpu(), torch.zeros(B, Cin, *sp))  # max|dY| = 0: scale 1
+
+
 def test_tc_rejects_unsupported_shapes_loudly():
+    RB = inb200.ResidualBlock(2, 128, n_out=4, k1=3, k2=3, p1=1, p2=1, precision="fp16x3", device=DEV)
+    with pytest.raises(inb200.InbError, match="fp16x3"):
+        RB.forward(g(torch.randn(1, 2, 16, 16)))
     RB = inb200.ResidualBlock(2, 32, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
     with pytest.raises(inb200.InbError, match="n_hidden"):
         RB.forward(g(torch.randn(1, 2, 16, 16)))
@@ -120,7 +146,7 @@ def test_tc_rejects_unsupported_shapes_loudly():
         RB.forward(g(torch.randn(1, 2, 12, 12)))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "fp16x3"])
 @pytest.mark.parametrize("sp", [(16, 16), (8, 8, 8)])
 def test_resblock_exact_lattice(prec, sp):
     """Flip-free gradient parity: inputs and weights on an integer lattice with half-integer biases, so
