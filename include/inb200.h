@@ -114,6 +114,8 @@ int inb_comm_unique_id(char id[128]);
 int inb_comm_create(int nranks, int rank, const char id[128], inb_comm** comm);
 /* wrap an existing ncclComm_t (NCCL.jl: Communicator.handle; torch: ProcessGroupNCCL._comm_ptr()); not destroyed with the handle */
 int inb_comm_wrap(void* nccl_comm, inb_comm** comm);
+/* detach the communicator from every plan first (inb_glow_plan_set_comm(plan, NULL)): a plan's captured CUDA graphs hold
+ * the communicator's collectives, and NCCL requires them to be destroyed before ncclCommDestroy */
 int inb_comm_destroy(inb_comm* comm);
 int inb_comm_info(const inb_comm* comm, int* nranks, int* rank, long long* allreduce_calls, long long* allreduce_bytes);
 /* Attach a communicator to a plan (NULL detaches).  With a communicator attached

@@ -146,6 +146,7 @@ struct inb_plan : GraphCache {
   double* ld = nullptr;
   SideLane lane;
   DpComm* dp = nullptr;  // attached communicator (inb_glow_plan_set_comm), not owned
+  DpComm* dp_warm = nullptr;  // the communicator whose collectives have run once outside a capture
   std::vector<long long> numel;     // element count of every parameter (get_params order)
   std::vector<long long> flat_off;  // canonical flat layout: element offset of every parameter, 64-element aligned
   long long flat_total = 0;
@@ -647,13 +648,23 @@ static bool graphs_enabled() {
 // private stream (nothing executes during capture), instantiate, launch on the caller's stream; later calls
 // with the same key: one cudaGraphLaunch.  Falls back to direct launches while profiling, inside a caller's own
 // capture, or with INB_GRAPHS=0.
+// With a communicator attached, the first backward of a plan is launched kernel by kernel: NCCL sets up its channels and
+// buffers for the message sizes of this plan on first use, which must not happen inside a stream capture.
+static bool dp_needs_warmup(inb_plan* p, int slot) {
+  if (!p->dp || p->dp->nranks <= 1 || slot != 2) return false;
+  if (p->dp_warm == p->dp) return false;
+  p->dp_warm = p->dp;
+  return true;
+}
+template <class Plan>
+static bool dp_needs_warmup(Plan*, int) { return false; }
 template <class Plan, class F>
 static void run_graphed(Plan* p, int slot, uint64_t key, void* stream, F&& enqueue) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
   cudaGetLastError();
-  if (!graphs_enabled() || capturing || prof_is_enabled()) {
+  if (!graphs_enabled() || capturing || prof_is_enabled() || dp_needs_warmup(p, slot)) {
     Ctx c = call_ctx(p, stream);
     enqueue(c);
     return;
@@ -851,6 +862,12 @@ int inb_comm_info(const inb_comm* comm, int* nranks, int* rank, long long* allre
 int inb_glow_plan_set_comm(inb_plan* p, inb_comm* comm) {
   return guarded([&] {
     INB_CHECK(p != nullptr, "null plan");
+    if (p->dp != comm) {
+      // graphs captured with the previous communicator hold its collectives: NCCL requires them to be destroyed
+      // before the communicator is (ncclCommDestroy otherwise waits for them forever)
+      for (auto& g : p->graphs[2])
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.key = 0; }
+    }
     p->dp = comm;
   });
 }

@@ -79,6 +79,7 @@ class Communicator:
 
     def __init__(self, handle: ctypes.c_void_p):
         self._h = handle
+        self._attached = []  # weak references to the networks this communicator is attached to
 
     @staticmethod
     def unique_id() -> bytes:
@@ -118,7 +119,14 @@ class Communicator:
         return {"nranks": n.value, "rank": r.value, "allreduce_calls": calls.value, "allreduce_bytes": nbytes.value}
 
     def destroy(self):
+        """Detaches from every network first: a plan's captured graphs hold the communicator's collectives and NCCL
+        wants them gone before ncclCommDestroy."""
         if self._h:
+            for ref in self._attached:
+                G = ref()
+                if G is not None and getattr(G, "_comm", None) is self:
+                    attach(G, None)
+            self._attached = []
             _l.load().inb_comm_destroy(self._h)
             self._h = None
 
@@ -126,7 +134,10 @@ class Communicator:
 def attach(G, comm: Optional[Communicator]) -> None:
     """inb_glow_plan_set_comm for the network's plan (now and whenever the plan is rebuilt): global-batch ActNorm
     initialisation in the first forward, per-scale overlapped gradient averaging in backward."""
+    import weakref
     G._comm = comm
+    if comm is not None:
+        comm._attached.append(weakref.ref(G))
     if getattr(G, "_plan", None) is not None:
         _l.call("inb_glow_plan_set_comm", G._plan, comm._h if comm is not None else None)
 

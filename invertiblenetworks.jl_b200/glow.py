@@ -53,15 +53,20 @@ def set_params(obj, new: Sequence) -> None:
     ps = obj.get_params()
     if len(ps) != len(new):
         raise ValueError("parameter count mismatch")
-    for p, q in zip(ps, new):
+    n_an = getattr(obj, "_n_an", 0)
+    an_given = n_an > 0
+    for i, (p, q) in enumerate(zip(ps, new)):
         src = q.data if isinstance(q, Parameter) else q
         if src is None:
+            if i < n_an:
+                an_given = False
             continue
         src = src.to(device=p.data.device, dtype=torch.float32)
         if p.data.shape != src.shape:
             raise ValueError(f"parameter shape mismatch {tuple(p.data.shape)} vs {tuple(src.shape)}")
         p.data.copy_(src)
-    if hasattr(obj, "_mark_initialized"):
+    # the data-dependent ActNorm initialisation is skipped only when every s, b was actually supplied
+    if an_given and hasattr(obj, "_mark_initialized"):
         obj._mark_initialized()
 
 
@@ -71,6 +76,9 @@ def save_params(obj, path: str) -> None:
     Here: one .npz with arrays p000, p001, ... in get_params order, stored in the REFERENCE's axis order - a torch tensor
     (Cout, Cin, ky, kx) is written as the Julia array (kx, ky, Cin, Cout), so `NPZ.npzread` + `set_params!` loads it."""
     import numpy as np
+    if hasattr(obj, "_an_ready") and not obj._an_ready:
+        raise _l.InbError("save_params: ActNorm is still uninitialised (run one forward first); its s, b are "
+                          "data-dependent (invertible_layer_actnorm.jl:67-72) and would be saved as zeros")
     arrs = {}
     for i, p in enumerate(obj.get_params()):
         a = p.data.detach().cpu().numpy()
@@ -81,6 +89,9 @@ def save_params(obj, path: str) -> None:
 def load_params(obj, path: str) -> None:
     """Inverse of save_params (set_params! semantics: shapes must match the architecture)."""
     import numpy as np
+    import os
+    if not os.path.exists(path) and os.path.exists(path + ".npz"):
+        path = path + ".npz"  # numpy.savez appends the suffix when it is missing
     z = np.load(path)
     ps = obj.get_params()
     if len(z.files) != len(ps):
@@ -401,6 +412,7 @@ class _GlowBase:
             o += (n + 63) // 64 * 64
         self.flat_params = torch.zeros(o, device=self.device)
         self.flat_grads = torch.zeros(o, device=self.device)
+        self._slots = list(zip(offs, sizes, shapes))
         self._params = [Parameter(self.flat_params[a:a + n].view(s)) for a, n, s in zip(offs, sizes, shapes)]
         self._gviews = [self.flat_grads[a:a + n].view(s) for a, n, s in zip(offs, sizes, shapes)]
         self._tabs = None  # (params, grads) device-pointer tables, built on first use
@@ -424,6 +436,17 @@ class _GlowBase:
 
     @property
     def _ptab(self):
+        # The library, the optimiser and the data-parallel all-reduce work on the flat buffers.  The reference idiom
+        # `p.data = new_array` (parameter.jl:73-76 does it in set_params!) is honoured by copying a rebound array back
+        # into the parameter's slot of the flat buffer (same shape required), so views and pointer tables stay valid.
+        for p, (a, n, shp) in zip(self._params, self._slots):
+            d = p.data
+            if d is None or d.data_ptr() != self.flat_params.data_ptr() + 4 * a:
+                if d is None or tuple(d.shape) != tuple(shp):
+                    raise _l.InbError("a network parameter was replaced by an array of another shape (or None)")
+                view = self.flat_params[a:a + n].view(shp)
+                view.copy_(d.to(device=self.device, dtype=torch.float32))
+                p.data = view
         if self._tabs is None:
             self._tabs = (_l.ptr_table([p.data for p in self._params]), _l.ptr_table(self._gviews))
         return self._tabs[0]

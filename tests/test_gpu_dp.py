@@ -91,6 +91,7 @@ def _worker(rank, world, port, precision, out):
             out["explicit_vs_attached"] = _rel(explicit, res[0])
             out["graph"] = dict(stats)
             out["comm"] = dict(info)
+        dist.barrier()
         comm.destroy()
     finally:
         dist.destroy_process_group()
