@@ -450,7 +450,7 @@ static void drive_reverse(inb_plan* p, Ctx& c, int B, bool grads, const float* d
     // step leave the main stream and overlap the next step.  The steps then alternate between two workspace regions
     // (the second starts `foot` bytes above the first), and a region is reused only after its gradients are done.
     size_t foot = 0;
-    if (grads && pre_b && (long long)B * s.g.px / 512 <= 74 && wgrad_defer_enabled()) {
+    if (grads && pre_b && ((long long)B * s.g.px / 512 <= 74 || wgrad_overlap_ctas() > 0) && wgrad_defer_enabled()) {
       Arena tmp;
       tmp.dry = true;
       Ctx tc{nullptr, &tmp, c.prec};

@@ -89,8 +89,10 @@ struct Wgrad2TcSpec {
   float* dw;
   float* db;
   const uint32_t* smax = nullptr;  // INB_PREC_FP16X3: one operand carries the gradient scale; the reduction divides by it
+  int np_real = 0;                 // rows of dw / db that exist (P padded with zero channels up to np); 0 = np
 };
 void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
+int wgrad_overlap_ctas();  // CTAs per weight-gradient kernel when they run under the next step's chain passes (0 = off)
 void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n);  // one reduction launch for up to three gradients
 
 // Fused pass of the block's three contractions (conv_tc_chain.cu): im2col-GEMM -> per-pixel GEMM ->
@@ -99,7 +101,8 @@ struct ChainSpec {
   Geo g;
   int B;
   int k1;
-  int nh;
+  int nh;             // hidden channels of the planes: 128 or 256 (n_hidden padded with zero channels, chain_nh_pad)
+  int nh_real;        // the block's n_hidden (length of the bias vectors); 0 = nh
   Planes in;          // im2col rows [M][kp], pitch = kp (multiple of 64)
   Planes w1, w2, w3;  // [nh][kp], [nh][nh] (+I), tap-expanded [n3pad][nh]
   int Cn;             // real output channels of the last contraction
@@ -116,10 +119,12 @@ struct ChainSpec {
   const uint32_t* smax = nullptr;  // INB_PREC_FP16X3 backward pass: the scale of `in` (col2im divides by it)
 };
 int chain_n3pad(int taps, int Cn);
+inline int chain_nh_pad(int nh) { return nh <= 128 ? 128 : 256; }  // hidden width the chain kernels run at
 int chain_kpad(int taps, int C, int extra);  // im2col width: taps*C (+ extra columns) rounded up to 64
 bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn);
 // the three packed operands of one chain pass in a single launch (conv_tc_chain.cu: k_pack_chain_tc)
-void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
+// nh = padded hidden width of the planes, nhr = the block's n_hidden (rows / columns beyond it are zero)
+void op_pack_chain_tc(Ctx& c, int nh, int nhr, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
                       int n3pad, const float* wc, Planes w1, Planes w2, Planes w3);
 // the same packing for several blocks of one shape in ONE launch (the K flow steps of a scale: their weights do not
 // change during a network-level call, so all of them are packed before the first step runs)
@@ -127,8 +132,8 @@ struct PackChainItem {
   const float *wa, *wb, *wc;
   Planes w1, w2, w3;
 };
-void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int Cn, int n3pad, const PackChainItem* items,
-                         int n);
+void op_pack_chain_multi(Ctx& c, int nh, int nhr, int T, int C1, int kp, int w2_data, int Cn, int n3pad,
+                         const PackChainItem* items, int n);
 void op_rb_chain(Ctx& c, const ChainSpec& s);
 void chain_set_trace(long long* p);
 

@@ -42,6 +42,7 @@ struct ChainArgs {
   int ntiles;
   int nkb1;               // GEMM1 k-blocks of 64 im2col columns
   int nh, nchunk;         // hidden channels (128 | 256), nh / 64
+  int nh_bias;            // entries of the bias vectors (the block's n_hidden; channels beyond it are padding)
   int n3a, n3b, n3pad;    // GEMM3 columns in R0 / R1 and the pitch of P (multiple of 16)
   int np3;                // 128-column pieces of GEMM3
   int stages;
@@ -166,7 +167,7 @@ k_rb_chain(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     const float* bp = (i < 256) ? a.bias1 : a.bias2;
     const int j = i & 255;
-    sbias[i] = (bp && j < a.nh) ? bp[j] : 0.f;
+    sbias[i] = (bp && j < a.nh_bias) ? bp[j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -511,7 +512,7 @@ k_rb_chain_t(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     const float* bp = (i < 256) ? a.bias1 : a.bias2;
     const int j = i & 255;
-    sbias[i] = (bp && j < a.nh) ? bp[j] : 0.f;
+    sbias[i] = (bp && j < a.nh_bias) ? bp[j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -997,7 +998,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   for (int i = threadIdx.x; i < 512; i += blockDim.x) {
     const float* bp = (i < 256) ? a.bias1 : a.bias2;
     const int j = i & 255;
-    sbias[i] = (bp && j < a.nh) ? bp[j] : 0.f;
+    sbias[i] = (bp && j < a.nh_bias) ? bp[j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -1629,6 +1630,7 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
 // (wa = W1, wc = W3 in the forward pass; wa = W3, wc = W1 in the backward pass; reference layout w[d0][d1][T])
 struct PackChainArgs {
   int f16;       // INB_PREC_FP16X3: IEEE-half planes of kF16WScale * w
+  int nhr;       // the block's n_hidden: the reference arrays have nhr hidden channels, the planes nh (zero padded)
   int nh, T, C1, kp, Cn, n3pad, w2_data;
   const float *wa, *wb, *wc;
   __nv_bfloat16 *w1h, *w1l, *w2h, *w2l, *w3h, *w3l;
@@ -1643,7 +1645,7 @@ __global__ void k_pack_chain_tc(const PackChainArgs a) {
     if (i < n1) {
       o = i;
       const int k = (int)(i % a.kp), n = (int)(i / a.kp);
-      if (k < a.T * a.C1) {
+      if (k < a.T * a.C1 && n < a.nhr) {
         const int tap = k / a.C1, cc = k - tap * a.C1;
         v = a.wa[((long long)n * a.C1 + cc) * a.T + (a.T - 1 - tap)];
       }
@@ -1651,13 +1653,15 @@ __global__ void k_pack_chain_tc(const PackChainArgs a) {
     } else if (i < n1 + n2) {
       o = i - n1;
       const int cc = (int)(o % a.nh), n = (int)(o / a.nh);
-      v = a.w2_data ? a.wb[(long long)cc * a.nh + n] : a.wb[(long long)n * a.nh + cc];
-      if (n == cc) v += 1.f;
+      if (n < a.nhr && cc < a.nhr) {
+        v = a.w2_data ? a.wb[(long long)cc * a.nhr + n] : a.wb[(long long)n * a.nhr + cc];
+        if (n == cc) v += 1.f;
+      }
       dh = a.w2h; dl = a.w2l;
     } else {
       o = i - n1 - n2;
       const int c = (int)(o % a.nh), r = (int)(o / a.nh);
-      if (r < a.T * a.Cn) {
+      if (r < a.T * a.Cn && c < a.nhr) {
         const int tap = r / a.Cn, n = r - tap * a.Cn;
         v = a.wc[((long long)c * a.Cn + n) * a.T + tap];
       }
@@ -1679,6 +1683,7 @@ __global__ void k_pack_chain_tc(const PackChainArgs a) {
 constexpr int kPackMulti = 24;
 struct PackMultiArgs {
   int f16;
+  int nhr;
   int nh, T, C1, kp, Cn, n3pad, w2_data, n, blocks_per_item;
   const float* wa[kPackMulti];
   const float* wb[kPackMulti];
@@ -1696,7 +1701,7 @@ __global__ void k_pack_chain_multi(const __grid_constant__ PackMultiArgs a) {
     if (i < n1) {
       o = i;
       const int k = (int)(i % a.kp), n = (int)(i / a.kp);
-      if (k < a.T * a.C1) {
+      if (k < a.T * a.C1 && n < a.nhr) {
         const int tap = k / a.C1, cc = k - tap * a.C1;
         v = wa[((long long)n * a.C1 + cc) * a.T + (a.T - 1 - tap)];
       }
@@ -1704,13 +1709,15 @@ __global__ void k_pack_chain_multi(const __grid_constant__ PackMultiArgs a) {
     } else if (i < n1 + n2) {
       o = i - n1;
       const int cc = (int)(o % a.nh), n = (int)(o / a.nh);
-      v = a.w2_data ? wb[(long long)cc * a.nh + n] : wb[(long long)n * a.nh + cc];
-      if (n == cc) v += 1.f;
+      if (n < a.nhr && cc < a.nhr) {
+        v = a.w2_data ? wb[(long long)cc * a.nhr + n] : wb[(long long)n * a.nhr + cc];
+        if (n == cc) v += 1.f;
+      }
       which = 2;
     } else {
       o = i - n1 - n2;
       const int c = (int)(o % a.nh), r = (int)(o / a.nh);
-      if (r < a.T * a.Cn) {
+      if (r < a.T * a.Cn && c < a.nhr) {
         const int tap = r / a.Cn, n = r - tap * a.Cn;
         v = wc[((long long)c * a.Cn + n) * a.T + tap];
       }
@@ -1729,13 +1736,14 @@ __global__ void k_pack_chain_multi(const __grid_constant__ PackMultiArgs a) {
     }
   }
 }
-void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int Cn, int n3pad, const PackChainItem* items,
-                         int n) {
+void op_pack_chain_multi(Ctx& c, int nh, int nhr, int T, int C1, int kp, int w2_data, int Cn, int n3pad,
+                         const PackChainItem* items, int n) {
   if (c.dry()) return;
   const long long per = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
   for (int i0 = 0; i0 < n; i0 += kPackMulti) {
     PackMultiArgs a{};
     a.f16 = prec_f16(c.prec) ? 1 : 0;
+    a.nhr = nhr;
     a.nh = nh; a.T = T; a.C1 = C1; a.kp = kp; a.Cn = Cn; a.n3pad = n3pad; a.w2_data = w2_data;
     a.n = std::min(kPackMulti, n - i0);
     a.blocks_per_item = (int)std::min<long long>(cdiv(per, 256), 64);
@@ -1750,10 +1758,10 @@ void op_pack_chain_multi(Ctx& c, int nh, int T, int C1, int kp, int w2_data, int
     INB_CUDA(cudaGetLastError());
   }
 }
-void op_pack_chain_tc(Ctx& c, int nh, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
+void op_pack_chain_tc(Ctx& c, int nh, int nhr, int T, int C1, int kp, const float* wa, const float* wb, int w2_data, int Cn,
                       int n3pad, const float* wc, Planes w1, Planes w2, Planes w3) {
   if (c.dry()) return;
-  PackChainArgs a{prec_f16(c.prec) ? 1 : 0, nh, T, C1, kp, Cn, n3pad, w2_data, wa, wb, wc, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo};
+  PackChainArgs a{prec_f16(c.prec) ? 1 : 0, nhr, nh, T, C1, kp, Cn, n3pad, w2_data, wa, wb, wc, w1.hi, w1.lo, w2.hi, w2.lo, w3.hi, w3.lo};
   const long long n = (long long)nh * kp + (long long)nh * nh + (long long)n3pad * nh;
   Prof pf(c, F_PACK, 1, 0, 8.0 * n);
   k_pack_chain_tc<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 8), 256, 0, c.st>>>(a);
@@ -1767,20 +1775,24 @@ void chain_set_trace(long long* p) { g_chain_trace = p; g_chain_trace_launch = 0
 
 // columns of the tap-expanded GEMM: a multiple of 16; beyond 256 a multiple of 32, so that the CTA-pair kernel can run
 // it as two equal passes of a multiple of 16 columns
+// beyond 256 columns the CTA-pair kernel runs GEMM3 in ceil(n / 256) equal passes of a multiple of 16 columns each
+// through the same TMEM region (cfg2 scale 3: 432 -> 2 x 224; 3-D blocks with 27 taps x 32 channels: 864 -> 4 x 224)
 int chain_n3pad(int taps, int Cn) {
   const int n = (taps * Cn + 15) / 16 * 16;
-  return n <= 256 ? n : (n + 31) / 32 * 32;
+  if (n <= 256) return n;
+  const int pieces = (n + 255) / 256;
+  return (n + 16 * pieces - 1) / (16 * pieces) * (16 * pieces);
 }
 
 int chain_kpad(int taps, int C, int extra) { return (taps * C + extra + 63) / 64 * 64; }
 
 bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn) {
   if (k2 != 1) return false;
-  if (nh != 128 && nh != 256) return false;
+  if (nh < 1 || nh > 256) return false;  // runs at 128 or 256 hidden channels (chain_nh_pad), smaller blocks zero padded
   const int taps = k1 == 1 ? 1 : (g.nd == 3 ? 27 : 9);
   if (chain_kpad(taps, C_in, 1) > 1024) return false;
   const int n3 = chain_n3pad(taps, Cn);
-  if (n3 > 480 || Cn > 128) return false;
+  if (n3 > 1024 || Cn > 128) return false;
   (void)B;
   return true;
 }
@@ -1798,7 +1810,9 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.M = s.g.px * s.B;
   a.ntiles = (int)cdiv(a.M, 128);
   a.nkb1 = s.in.pitch / 64;
+  INB_CHECK(s.nh == 128 || s.nh == 256, "fused ResidualBlock chain: the planes have 128 or 256 hidden channels");
   a.nh = s.nh;
+  a.nh_bias = s.nh_real > 0 ? s.nh_real : s.nh;
   a.nchunk = s.nh / 64;
   a.n3pad = chain_n3pad(taps, s.Cn);
   a.n3a = std::min(a.n3pad, 256);
@@ -1825,10 +1839,10 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     if (!e) e = getenv("INB_CHAIN_SMEM") && getenv("INB_CHAIN_SMEM")[0] == '1' ? "smem" : "";
     return e[0] == 't' ? 1 : (e[0] == 's' ? 2 : 0);
   }();
-  const bool pair = (a.n3pad <= 256 || (a.n3pad <= 512 && a.n3pad % 32 == 0)) && force == 0;
-  INB_CHECK(pair || !f16, "precision fp16x3 runs on the CTA-pair chain kernel only (use bf16x3 for this shape)");
-  a.npiece = a.n3pad <= 256 ? 1 : 2;
+  a.npiece = (a.n3pad + 255) / 256;
   a.n3piece = a.n3pad / a.npiece;
+  const bool pair = (a.n3pad % (16 * a.npiece) == 0) && force == 0;
+  INB_CHECK(pair || (!f16 && a.n3pad <= 480), "fused ResidualBlock chain: %d expanded columns need the CTA-pair kernel", a.n3pad);
   static const bool no_qsum = [] { const char* e = getenv("INB_CHAIN_QSUM"); return e && e[0] == '0'; }();
   a.Cn = s.Cn;
   a.cq = (s.Cn + 3) / 4 * 4;
@@ -1888,6 +1902,10 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
         mpairs = std::min(n, 74);
       }
       int use_pairs = mpairs;
+      {  // SMs left to the weight-gradient kernels that run under this pass (conv_tc_wgrad2.cu: wgrad_overlap_ctas)
+        const int w = wgrad_overlap_ctas();
+        if (w > 0 && c.lane && a.ntiles >= 4 * 148) use_pairs = std::max(8, std::min(use_pairs, (148 - 3 * w) / 2));
+      }
       if (const char* e = getenv("INB_CHAIN_MAXPAIRS")) {  // tests: few resident pairs = many tiles per pair on small inputs
         const int v = atoi(e);
         if (v > 0 && v < use_pairs) use_pairs = v;

@@ -19,6 +19,7 @@
 #include "tc_maps.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace inb {
 using namespace tc;
@@ -199,6 +200,7 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
 struct WgradReduceDesc {
   const float* part;
   int ncta, np, pitch, C, T;
+  int np_real;  // rows p >= np_real are zero padding of the hidden width: not part of dw / db
   float* dw;
   const float* dbpart;
   float* db;
@@ -213,7 +215,8 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
   const float* __restrict__ dbpart = q.dbpart;
   const int ncta = q.ncta, np = q.np, pitch = q.pitch, C = q.C, T = q.T;
   const int ncol = T * C;
-  const long long total = (long long)np * ncol, outs = total + (dbpart ? np : 0);
+  const int npr = q.np_real;
+  const long long total = (long long)npr * ncol, outs = total + (dbpart ? npr : 0);
   float osc = 1.f;
   if (q.smax) { float sc; f16_scale_from_max(__ldg(q.smax), sc, osc); }
   const int sub = threadIdx.x >> 6;  // which quarter of the partials (a warp works on 32 consecutive outputs)
@@ -257,6 +260,19 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
   }
 }
 
+// Large batches: the weight gradients are HBM-bound (they read every stored hidden plane once) while the chain passes
+// around them are tensor-bound, so instead of taking turns on all SMs the three split-K kernels of a step run on
+// `wgrad_overlap_ctas()` CTAs each, on the side streams, UNDER the chain passes of the next flow step, which leave
+// those SMs free (op_rb_chain caps its resident pairs accordingly).  0 = off.  INB_WGRAD_OVERLAP=<ctas per kernel>.
+int wgrad_overlap_ctas() {
+  static const int n = [] {
+    const char* e = getenv("INB_WGRAD_OVERLAP");
+    const int v = e ? atoi(e) : 0;
+    return v < 0 ? 0 : (v > 48 ? 48 : v);
+  }();
+  return n;
+}
+
 // launches the split-K kernel of one weight gradient; its partial tiles stay allocated (the caller releases the arena
 // scope after the reduction) and are described in `rd`; returns the number of outputs
 static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& rd) {
@@ -286,7 +302,8 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   a.stages = stages;
   // split-K over the SMs, but at least 16 k-blocks (512 pixels) per CTA: every CTA costs a partial tile that the
   // reduction has to read back, which dominates when the batch shard is small
-  const int ctas = std::max(1, std::min(148 / ng, a.nblocks / 16));
+  int ctas = std::max(1, std::min(148 / ng, a.nblocks / 16));
+  if (c.wg_defer && wgrad_overlap_ctas() > 0) ctas = std::max(1, std::min(ctas, wgrad_overlap_ctas() / ng));
   a.blocks_per_cta = (int)cdiv(a.nblocks, ctas);
   const unsigned gx = (unsigned)cdiv(a.nblocks, a.blocks_per_cta);  // every CTA owns at least one block
   // scratch: partial tiles [ng][gx][np][nqmax] and partial bias sums [gx][np]
@@ -310,8 +327,9 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
     k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   }
   INB_CUDA(cudaGetLastError());
-  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, s.dw, a.dbpart, s.db, prec_f16(c.prec) ? s.smax : nullptr};
-  return (long long)s.np * s.T * s.C + (s.db ? s.np : 0);
+  const int npr = s.np_real > 0 ? s.np_real : s.np;
+  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, npr, s.dw, a.dbpart, s.db, prec_f16(c.prec) ? s.smax : nullptr};
+  return (long long)npr * s.T * s.C + (s.db ? npr : 0);
 }
 
 // n (<= 3) weight gradients: their split-K kernels back to back, then ONE reduction launch (grid row = gradient)
@@ -325,7 +343,8 @@ void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n) {
   // branches of the captured graph - and the reduction follows their join.
   SideLane* L = c.lane;
   const bool side_by_side = !c.dry() && n == 3 && L && L->wst[0] && L->wnext + 3 <= L->nwev &&
-                            specs[0].M / (kWgPB * 16) <= 74 && specs[0].M == specs[1].M && specs[0].M == specs[2].M;
+                            (specs[0].M / (kWgPB * 16) <= 74 || (c.wg_defer && wgrad_overlap_ctas() > 0)) &&
+                            specs[0].M == specs[1].M && specs[0].M == specs[2].M;
   if (side_by_side && c.wg_defer && L->wst[2] && L->wnext + 4 <= L->nwev) {
     // all three off the main stream; nothing on the main stream waits for them before the region is reused
     cudaEvent_t ef = L->wev[L->wnext], e1 = L->wev[L->wnext + 1], e2 = L->wev[L->wnext + 2], ed = L->wev[L->wnext + 3];

@@ -914,8 +914,9 @@ template <int V>
 __global__ void k_coupling_bwd(const float* __restrict__ y1, long long ybs, float* __restrict__ x1,
                                long long xbs, const float* __restrict__ dy1, long long dybs,
                                float* __restrict__ dx1, long long dxbs, float* __restrict__ rb,
-                               long long px, int C1, float low, float high, float invB) {
+                               long long px, int C1, float low, float high, float invB, unsigned* __restrict__ amax) {
   const int ch = blockIdx.y;
+  float gmax = 0.f;  // max |gradient of the block output| seen by this thread (INB_PREC_FP16X3 scales by it)
   const long long b = blockIdx.z;
   const long long pxv = px / V;
   const float* yp = y1 + b * ybs + ch * px;
@@ -946,11 +947,17 @@ __global__ void k_coupling_bwd(const float* __restrict__ y1, long long ybs, floa
       // _relugrad of the block's output ReLU (activation_functions.jl:84): pass when pre-activation >= 0
       gl[u] = (ls[u] < 0.f) ? 0.f : dl;
       gt[u] = (tv[u] < 0.f) ? 0.f : dyv[u];  // dT = dY1 (glow.jl:143)
+      gmax = fmaxf(gmax, fmaxf(fabsf(gl[u]), fabsf(gt[u])));
     }
     stv<V>(xp + pix, xo);
     stv<V>(dxp + pix, dxo);
     stv<V>(plsb + pix, gl);
     stv<V>(ptvb + pix, gt);
+  }
+  if (amax) {  // bit patterns of non-negative floats are ordered like the values
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+    if ((threadIdx.x & 31) == 0 && gmax > 0.f) atomicMax(amax, __float_as_uint(gmax));
   }
 }
 
@@ -994,15 +1001,15 @@ void op_coupling_inv(Ctx& c, long long px, int B, int C1, View y1, View x1, cons
   INB_CUDA(cudaGetLastError());
 }
 void op_coupling_bwd(Ctx& c, long long px, int B, int C1, View y1, View x1, View dy1, View dx1,
-                     float* rb, float low, float high, int logdet) {
+                     float* rb, float low, float high, int logdet, unsigned* amax) {
   if (c.dry()) return;
   Prof pf(c, F_COUPLING_BWD, 1, 0, 32.0 * B * C1 * px);
   int V = pick_vec_ew(px, {&x1, &y1, &dy1, &dx1}, rb);
   const dim3 grid = coupling_grid(px / V, C1, B);
   float invB = logdet ? 1.f / (float)B : 0.f;
-  if (V == 4) k_coupling_bwd<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
-  else if (V == 2) k_coupling_bwd<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
-  else k_coupling_bwd<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB);
+  if (V == 4) k_coupling_bwd<4><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB, amax);
+  else if (V == 2) k_coupling_bwd<2><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB, amax);
+  else k_coupling_bwd<1><<<grid, 256, 0, c.st>>>(y1.p, y1.bs, x1.p, x1.bs, dy1.p, dy1.bs, dx1.p, dx1.bs, rb, px, C1, low, high, invB, amax);
   INB_CUDA(cudaGetLastError());
 }
 

@@ -40,6 +40,9 @@ struct RBHidden {
   // fused-chain path: relu-grad masks of Y1 / Y2 as bit planes [M][nh/32], written by the storing forward pass
   uint32_t* bm1 = nullptr;
   uint32_t* bm2 = nullptr;
+  // INB_PREC_FP16X3: device word with the bits of max|dY3|, when the producer of dY3 already reduced it (the coupling
+  // backward kernel does); rb_backward computes it with a pass over dY3 otherwise
+  uint32_t* dy_absmax = nullptr;
 };
 
 // layer_residual_block.jl:119-134, output = PRE-activation Y3 (B, Cout, px) compact; the consumers

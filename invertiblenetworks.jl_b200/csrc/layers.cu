@@ -5,7 +5,12 @@
 
 namespace inb {
 
-size_t rb_hidden_elems(const RBShape& s) { return (size_t)s.B * s.nh * s.g.px; }
+// hidden buffers hold (B, nh, px) fp32 on the CUDA-core path and bf16 / half hi+lo planes [M][nh padded to 128 | 256]
+// (same bytes per channel) on the fused tensor-core chain
+size_t rb_hidden_elems(const RBShape& s) {
+  const int nh = s.nh <= 256 ? chain_nh_pad(s.nh) : s.nh;
+  return (size_t)s.B * nh * s.g.px;
+}
 
 static ConvSpec conv_base(const RBShape& s) {
   ConvSpec cs{};
@@ -142,14 +147,25 @@ static void rb_backward_fp32(Ctx& c, const RBShape& s, const float* dY3, View x2
 static int pad16(int n) { return (n + 15) / 16 * 16; }
 
 static bool rb_chain_ok(const RBShape& s);
-static void tc_check(const RBShape& s, int prec = 1) {
-  INB_CHECK(!prec_f16(prec) || rb_chain_ok(s),
-            "precision fp16x3 needs the fused ResidualBlock chain (k2 = 1, n_hidden in {128, 256}); use bf16x3 or fp32");
-  INB_CHECK(s.nh % 128 == 0 && s.nh <= 256,
-            "the tensor-core path needs n_hidden in {128, 256} (got %d); use precision fp32", s.nh);
-  INB_CHECK(pad16(s.Cin()) <= 256 && pad16(s.Cout) <= 256, "the tensor-core path supports up to 256 channels");
-  INB_CHECK(tc_geometry_ok(s.g, s.B),
-            "spatial size %dx%dx%d cannot be tiled for the tensor-core path; use precision fp32", s.g.W, s.g.H, s.g.D);
+// Which kernels run a block under a tensor-core precision mode: the fused chain (k2 = 1, any n_hidden <= 256: blocks
+// narrower than 128 / 256 hidden channels are zero padded), else the unfused tensor-core convolutions (n_hidden in
+// {128, 256}; bf16 operands - under fp16x3 they compute in bf16x3), else - shapes neither can tile - the fp32
+// CUDA-core kernels.  A pure function of the shape: forward, recompute and backward of a block agree on it.
+enum { RB_PATH_SIMT = 0, RB_PATH_CHAIN = 1, RB_PATH_UNFUSED = 2 };
+static int rb_path(const Ctx& c, const RBShape& s) {
+  if (c.prec == 0) return RB_PATH_SIMT;
+  static const bool strict = [] { const char* e = getenv("INB_STRICT_TC"); return e && e[0] == '1'; }();
+  const bool geo = tc_geometry_ok(s.g, s.B);
+  if (geo && rb_chain_ok(s)) return RB_PATH_CHAIN;
+  const bool unfused = geo && s.nh % 128 == 0 && s.nh <= 256 && pad16(s.Cin()) <= 256 && pad16(s.Cout) <= 256;
+  if (unfused) return RB_PATH_UNFUSED;
+  if (strict) {
+    INB_CHECK(s.nh % 128 == 0 && s.nh <= 256,
+              "the tensor-core path needs n_hidden in {128, 256} (got %d) unless k2 = 1; use precision fp32", s.nh);
+    INB_CHECK(pad16(s.Cin()) <= 256 && pad16(s.Cout) <= 256, "the tensor-core path supports up to 256 channels");
+    INB_CHECK(geo, "spatial size %dx%dx%d cannot be tiled for the tensor-core path; use precision fp32", s.g.W, s.g.H, s.g.D);
+  }
+  return RB_PATH_SIMT;
 }
 static Planes planes_at(void* mem, long long M, int pitch) {
   Planes p;
@@ -167,8 +183,8 @@ static bool rb_chain_ok(const RBShape& s) {
          chain_supported(s.g, s.B, s.k1, s.k2, s.nh, s.Cout, s.Cin());
 }
 bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int direction, PackedW* out) {
-  if (c.prec == 0 || !rb_chain_ok(s) || n <= 0) return false;
-  const int T1 = s.T1(), nh = s.nh;
+  if (rb_path(c, s) != RB_PATH_CHAIN || n <= 0) return false;
+  const int T1 = s.T1(), nh = chain_nh_pad(s.nh);
   const int C1 = direction == 0 ? s.Cin() : s.Cout, Cn = direction == 0 ? s.Cout : s.Cin();
   const int kp = chain_kpad(T1, C1, 0), n3pad = chain_n3pad(T1, Cn);
   std::vector<PackChainItem> items(n);
@@ -181,7 +197,7 @@ bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int 
     items[i].wc = direction == 0 ? prm[i].W3 : prm[i].W1;
     items[i].w1 = out[i].w1; items[i].w2 = out[i].w2; items[i].w3 = out[i].w3;
   }
-  op_pack_chain_multi(c, nh, T1, C1, kp, direction, Cn, n3pad, items.data(), n);
+  op_pack_chain_multi(c, nh, s.nh, T1, C1, kp, direction, Cn, n3pad, items.data(), n);
   return true;
 }
 
@@ -194,11 +210,12 @@ static ConvTcSpec tc_base(const RBShape& s) {
 }
 
 static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
-  tc_check(s, c.prec);
   const long long px = s.g.px, M = px * s.B;
-  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2();
+  const int Cin = s.Cin(), T1 = s.T1(), T2 = s.T2();
   const int cin_pad = pad16(Cin), cout_pad = pad16(s.Cout);
-  if (rb_chain_ok(s)) {
+  const bool chain = rb_path(c, s) == RB_PATH_CHAIN;
+  const int nh = chain ? chain_nh_pad(s.nh) : s.nh;
+  if (chain) {
     // one fused kernel for the three contractions (conv_tc_chain.cu); the hidden tensors reach HBM only
     // when a backward pass follows (h.G != nullptr: the recompute of flow_backward).  The im2col rows of the
     // block input outlive this call: the weight gradient of conv1 reads them again.
@@ -218,10 +235,10 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     } else {
       W1 = planes_new(c, nh, kp); W2 = planes_new(c, nh, nh); W3 = planes_new(c, n3pad, nh);
       // conv(X, W1) | W2 + I (the skip of :125) | \nabla conv_data(., W3) tap-expanded
-      op_pack_chain_tc(c, nh, T1, Cin, kp, p.W1, p.W2, 0, s.Cout, n3pad, p.W3, W1, W2, W3);
+      op_pack_chain_tc(c, nh, s.nh, T1, Cin, kp, p.W1, p.W2, 0, s.Cout, n3pad, p.W3, W1, W2, W3);
     }
     ChainSpec cs{};
-    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
+    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh; cs.nh_real = s.nh;
     cs.in = h.xin; cs.w1 = W1; cs.w2 = W2; cs.w3 = W3; cs.Cn = s.Cout;
     cs.mode = 0; cs.bias1 = p.b1; cs.bias2 = p.b2;
     if (h.G) { cs.o1 = H1; cs.o2 = H2; cs.bits1 = h.bm1; cs.bits2 = h.bm2; }
@@ -265,13 +282,14 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
 static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
                            RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs,
                            View dcond) {
-  tc_check(s, c.prec);
   const long long px = s.g.px, M = px * s.B;
-  const int Cin = s.Cin(), nh = s.nh, T1 = s.T1(), T2 = s.T2(), Cout = s.Cout;
+  const int Cin = s.Cin(), T1 = s.T1(), T2 = s.T2(), Cout = s.Cout;
   const int cin_pad = pad16(Cin), cout_pad = pad16(Cout);
+  const bool chain = rb_path(c, s) == RB_PATH_CHAIN;
+  const int nh = chain ? chain_nh_pad(s.nh) : s.nh;
   size_t m = c.ar->mark();
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh), G2 = planes_at(h.G, M, nh);
-  if (rb_chain_ok(s)) {
+  if (chain) {
     // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the weight
     // gradients, which read every hidden tensor exactly once and produce the bias gradients on the way
     Planes G1 = planes_new(c, M, nh);
@@ -288,15 +306,18 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     // the device) keeps the half-precision planes in their normal range; col2im and the gradient reduction divide by it
     uint32_t* smax = nullptr;
     if (prec_f16(c.prec)) {
-      smax = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes(256));
-      op_zero(c, smax, 4);
-      op_absmax(c, px, s.B, Cout, dY3, (long long)Cout * px, smax);
+      smax = h.dy_absmax;
+      if (!smax) {
+        smax = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes(256));
+        op_zero(c, smax, 4);
+        op_absmax(c, px, s.B, Cout, dY3, (long long)Cout * px, smax);
+      }
     }
     op_im2col_tc(c, s.g, s.B, s.k1, dY3, (long long)Cout * px, Cout, nullptr, 0, Cout, kp, -1, dcol, smax);
     // conv(dY3, W3) :151 | \nabla conv_data(., W2) + I (the '+ dY2' of :155) | \nabla conv_data(., W1) tap-expanded :162
-    if (!p.pre[1]) op_pack_chain_tc(c, nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
+    if (!p.pre[1]) op_pack_chain_tc(c, nh, s.nh, T1, Cout, kp, p.W3, p.W2, 1, Cin, n3pad, p.W1, W3c, W2d, W1e);
     ChainSpec cs{};
-    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh;
+    cs.g = s.g; cs.B = s.B; cs.k1 = s.k1; cs.nh = nh; cs.nh_real = s.nh;
     cs.in = dcol; cs.w1 = W3c; cs.w2 = W2d; cs.w3 = W1e; cs.Cn = Cin;
     cs.mode = 1; cs.mask1 = h.bm2; cs.mask2 = h.bm1;                     // :154, :161
     cs.o1 = G2; cs.o2 = G1;
@@ -307,9 +328,9 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     cs.smax = smax;
     op_rb_chain(c, cs);
     const Wgrad2TcSpec wg[3] = {
-        Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr, smax},   // :152
-        Wgrad2TcSpec{M, G2, nh, H1, nh, 1, gr.W2, gr.b2, smax},           // :156-157
-        Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1, smax}};     // :163-164
+        Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr, smax, s.nh},   // :152
+        Wgrad2TcSpec{M, G2, nh, H1, s.nh, 1, gr.W2, gr.b2, smax, s.nh},         // :156-157 (columns beyond n_hidden dropped)
+        Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1, smax, s.nh}};     // :163-164
     op_wgrad2_tc_multi(c, wg, 3);
     c.ar->release(m);
     return;
@@ -371,12 +392,12 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
 }
 
 void rb_forward(Ctx& c, const RBShape& s, View x2, View cond, const RBParams& p, RBHidden& h, float* Y3) {
-  if (c.prec == 0) rb_forward_fp32(c, s, x2, cond, p, h, Y3);
+  if (rb_path(c, s) == RB_PATH_SIMT) rb_forward_fp32(c, s, x2, cond, p, h, Y3);
   else rb_forward_tc(c, s, x2, cond, p, h, Y3);
 }
 void rb_backward(Ctx& c, const RBShape& s, const float* dY3, View x2, View cond, const RBParams& p,
                  RBHidden& h, const RBGrads& gr, View dx2, const float* add, long long add_bs, View dcond) {
-  if (c.prec == 0) rb_backward_fp32(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
+  if (rb_path(c, s) == RB_PATH_SIMT) rb_backward_fp32(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
   else rb_backward_tc(c, s, dY3, x2, cond, p, h, gr, dx2, add, add_bs, dcond);
 }
 
@@ -440,7 +461,11 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
   // layer_residual_block.jl:143 - same values)
   rb_forward(c, rs, y2, cond, p.rb, h, Y3);
   // X1, dX1, and the masked gradient of the block output        glow.jl:127,142-151
-  op_coupling_bwd(c, px, f.B, C1, y, y, dy, dy, Y3, f.low, f.high, f.logdet);
+  if (prec_f16(c.prec)) {  // max|dY3| falls out of the kernel that writes dY3
+    h.dy_absmax = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes(256));
+    op_zero(c, h.dy_absmax, 4);
+  }
+  op_coupling_bwd(c, px, f.B, C1, y, y, dy, dy, Y3, f.low, f.high, f.logdet, h.dy_absmax);
   // dX2 = RB.backward(...) + dY2                                 glow.jl:151
   rb_backward(c, rs, Y3, y2, cond, p.rb, h, g.rb, dy2, dy2.p, dy2.bs, dcond);
   // Conv1x1 inverse on (dX_, X_) + ActNorm backward              glow.jl:159, actnorm.jl:100-123

@@ -47,8 +47,9 @@ void op_coupling_fwd(Ctx& c, long long px, int B, int C1, View x1, View y1, cons
 void op_coupling_inv(Ctx& c, long long px, int B, int C1, View y1, View x1, const float* rb, float low,
                      float high);
 // y1 -> x1, dy1 -> dx1 (views, in place allowed), rb (Y3) -> dY3 in place
+// amax (nullable): atomicMax of the bit patterns of |masked gradient of the block output| (zeroed by the caller)
 void op_coupling_bwd(Ctx& c, long long px, int B, int C1, View y1, View x1, View dy1, View dx1,
-                     float* rb, float low, float high, int logdet);
+                     float* rb, float low, float high, int logdet, unsigned* amax = nullptr);
 void op_relu_copy(Ctx& c, long long n, const float* in, float* out);
 // _relugrad (activation_functions.jl:84): out = y < 0 ? 0 : dy
 void op_relu_grad(Ctx& c, long long n, const float* dy, const float* y, float* out);

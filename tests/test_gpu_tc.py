@@ -39,8 +39,6 @@ def test_resblock_tc(case, prec):
     torch.manual_seed(4)
     tol_out, tol_grad = TOLS[prec]
     B, Cin, nh, Cout, sp, k1, k2 = case
-    if prec == "fp16x3" and k2 != 1:
-        pytest.skip("fp16x3 runs on the fused chain only (k2 = 1)")
     nd = len(sp)
     RB = inb200.ResidualBlock(Cin, nh, n_out=Cout, k1=k1, k2=k2, p1=(k1 - 1) // 2, p2=(k2 - 1) // 2, ndims=nd,
                               precision=prec, gen=torch.Generator().manual_seed(3), device=DEV)
@@ -134,16 +132,39 @@ def test_fp16x3_gradient_scale_covers_tiny_and_huge_gradients():
     assert torch.equal(RB.backward(g(dY * 0), g(X)).cpu(), torch.zeros(B, Cin, *sp))  # max|dY| = 0: scale 1
 
 
-def test_tc_rejects_unsupported_shapes_loudly():
-    RB = inb200.ResidualBlock(2, 128, n_out=4, k1=3, k2=3, p1=1, p2=1, precision="fp16x3", device=DEV)
-    with pytest.raises(inb200.InbError, match="fp16x3"):
-        RB.forward(g(torch.randn(1, 2, 16, 16)))
-    RB = inb200.ResidualBlock(2, 32, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
-    with pytest.raises(inb200.InbError, match="n_hidden"):
-        RB.forward(g(torch.randn(1, 2, 16, 16)))
-    RB = inb200.ResidualBlock(2, 128, n_out=4, k1=3, k2=1, p1=1, p2=0, precision="bf16x3", device=DEV)
-    with pytest.raises(inb200.InbError, match="tiled"):
-        RB.forward(g(torch.randn(1, 2, 12, 12)))
+SMALL_NH_CASES = [
+    # B, Cin, nh, Cout, spatial, k1, k2 - blocks narrower than the 128 hidden channels the chain kernels run at
+    (2, 2, 32, 4, (32, 32), 3, 1),         # cfg1 / cfg3 scale-1 plan (n_hidden = 32)
+    (2, 4, 64, 8, (16, 16), 3, 1),
+    (2, 5, 70, 6, (16, 16), 3, 1),         # not a multiple of anything
+    (2, 4, 32, 8, (8, 8, 8), 3, 1),        # cfg5 scale-1 plan (3-D, 27 taps)
+    (2, 6, 160, 12, (16, 16), 3, 1),       # between 128 and 256
+    (2, 16, 32, 32, (8, 8, 8), 3, 1),      # cfg5 scale-2 plan: 27 taps x 32 channels = 864 expanded columns, four GEMM3 passes
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("case", SMALL_NH_CASES)
+def test_resblock_tc_small_n_hidden(case, prec):
+    """n_hidden of 32 / 64 (BASELINE configs[0], [2], [4]) on the fused tcgen05 chain: the hidden width is zero padded
+    to 128 (or 256) inside the packed operands; outputs and all five gradients have the block's own shapes."""
+    test_resblock_tc(case, prec)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+def test_tc_modes_fall_back_for_shapes_the_tensor_core_kernels_cannot_tile(prec):
+    """A tensor-core precision never refuses a block: k2 = 3 runs on the unfused tcgen05 convolutions (bf16x3 arithmetic
+    under either mode), a spatial size that cannot be cut into 64 / 128-pixel boxes on the fp32 CUDA-core kernels."""
+    test_resblock_tc((2, 6, 128, 12, (16, 16), 3, 3), "bf16x3" if prec == "bf16x3" else "fp16x3")
+    torch.manual_seed(4)
+    RB = inb200.ResidualBlock(2, 32, n_out=4, k1=3, k2=1, p1=1, p2=0, precision=prec,
+                              gen=torch.Generator().manual_seed(3), device=DEV)
+    ws = [p.data.cpu().double() for p in RB.get_params()]
+    R64 = O.ResidualBlock(*ws, p1=1, p2=0)
+    X, dY = torch.randn(1, 2, 12, 12), torch.randn(1, 4, 12, 12)
+    assert rel(RB.forward(g(X)), R64.forward(X.double())) < 1e-6       # fp32 kernels
+    dX = RB.backward(g(dY), g(X))
+    assert rel(dX, R64.backward(dY.double(), X.double())) < 1e-5
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3", "fp16x3"])
