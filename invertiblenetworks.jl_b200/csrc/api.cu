@@ -107,6 +107,18 @@ struct ScaleInfo {
   int kc;       // channels that continue after the split (== C when no split)
 };
 
+// Identity of a captured call: batch, communicator and every pointer it was captured with, folded into two independent
+// 64-bit hashes (a replay with stale pointers would corrupt memory silently, so a single 64-bit hash is not enough)
+struct GraphKey {
+  uint64_t a = 0, b = 0;
+  bool operator==(const GraphKey& o) const { return a == o.a && b == o.b; }
+  bool operator!=(const GraphKey& o) const { return !(*this == o); }
+  void add(uint64_t v) {
+    a ^= v + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2);
+    b = (b ^ (v * 0xFF51AFD7ED558CCDull)) * 0xC4CEB9FE1A85EC53ull;
+    b ^= b >> 29;
+  }
+};
 // graph-replay state shared by the network plans (run_graphed)
 struct GraphCache {
   // CUDA graphs of the network-level calls (slot 0 forward, 1 inverse, 2 backward): a call with the same
@@ -115,7 +127,7 @@ struct GraphCache {
   // slot, least recently used replaced)
   static constexpr int kGraphWays = 8;
   struct GraphSlot {
-    uint64_t key = 0;
+    GraphKey key;
     cudaGraphExec_t exec = nullptr;
     long long launches = 0;
     unsigned long long used = 0;
@@ -622,20 +634,19 @@ static Ctx call_ctx(inb_plan* p, void* stream) {
 }
 
 // ---------------------------------------------------------------- CUDA-graph replay of whole-network calls
-static uint64_t mix(uint64_t h, uint64_t v) {
-  h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-  return h;
-}
-static uint64_t key_of(const inb_plan* p, int batch, std::initializer_list<const void*> ptrs, float* const* params,
+static GraphKey key_of(const inb_plan* p, int batch, std::initializer_list<const void*> ptrs, float* const* params,
                        float* const* grads) {
-  uint64_t h = mix(0x1234567ull, (uint64_t)batch);
-  h = mix(h, (uint64_t)(uintptr_t)p->dp);  // a graph captured with a communicator holds its collectives
-  for (const void* q : ptrs) h = mix(h, (uint64_t)(uintptr_t)q);
+  GraphKey k;
+  k.add(0x1234567ull);
+  k.add((uint64_t)batch);
+  k.add((uint64_t)(uintptr_t)p->dp);  // a graph captured with a communicator holds its collectives
+  for (const void* q : ptrs) k.add((uint64_t)(uintptr_t)q);
   const int n = 10 * p->d.L * p->d.K + (p->cond ? 2 : 0);
-  for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)params[i]);
+  for (int i = 0; i < n; ++i) k.add((uint64_t)(uintptr_t)params[i]);
   if (grads)
-    for (int i = 0; i < n; ++i) h = mix(h, (uint64_t)(uintptr_t)grads[i]);
-  return h | 1ull;
+    for (int i = 0; i < n; ++i) k.add((uint64_t)(uintptr_t)grads[i]);
+  k.a |= 1ull;
+  return k;
 }
 static bool graphs_enabled() {
   static const bool on = [] {
@@ -659,7 +670,7 @@ static bool dp_needs_warmup(inb_plan* p, int slot) {
 template <class Plan>
 static bool dp_needs_warmup(Plan*, int) { return false; }
 template <class Plan, class F>
-static void run_graphed(Plan* p, int slot, uint64_t key, void* stream, F&& enqueue) {
+static void run_graphed(Plan* p, int slot, GraphKey key, void* stream, F&& enqueue) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   const bool capturing = st != nullptr && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
@@ -866,7 +877,7 @@ int inb_glow_plan_set_comm(inb_plan* p, inb_comm* comm) {
       // graphs captured with the previous communicator hold its collectives: NCCL requires them to be destroyed
       // before the communicator is (ncclCommDestroy otherwise waits for them forever)
       for (auto& g : p->graphs[2])
-        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.key = 0; }
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.key = GraphKey(); }
     }
     p->dp = comm;
   });
@@ -1501,14 +1512,17 @@ static Ctx call_ctx(inb_hint_plan* p, void* stream) {
   p->ar.off = p->persist;
   return Ctx{(cudaStream_t)stream, &p->ar, p->d.precision};
 }
-static uint64_t hint_key(const inb_hint_plan* p, int batch, std::initializer_list<const void*> ptrs,
+static GraphKey hint_key(const inb_hint_plan* p, int batch, std::initializer_list<const void*> ptrs,
                          float* const* params, float* const* grads) {
-  uint64_t h = mix(0x48494e54ull, (uint64_t)batch);
-  for (const void* q : ptrs) h = mix(h, (uint64_t)(uintptr_t)q);
-  for (int i = 0; i < p->nparams; ++i) h = mix(h, (uint64_t)(uintptr_t)params[i]);
+  GraphKey k;
+  k.add(0x48494e54ull);
+  k.add((uint64_t)batch);
+  for (const void* q : ptrs) k.add((uint64_t)(uintptr_t)q);
+  for (int i = 0; i < p->nparams; ++i) k.add((uint64_t)(uintptr_t)params[i]);
   if (grads)
-    for (int i = 0; i < p->nparams; ++i) h = mix(h, (uint64_t)(uintptr_t)grads[i]);
-  return h | 1ull;
+    for (int i = 0; i < p->nparams; ++i) k.add((uint64_t)(uintptr_t)grads[i]);
+  k.a |= 1ull;
+  return k;
 }
 static void hint_check_call(inb_hint_plan* p, int batch) {
   INB_CHECK(p != nullptr, "null plan");

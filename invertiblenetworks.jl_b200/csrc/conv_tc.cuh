@@ -95,6 +95,22 @@ void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
 int wgrad_overlap_ctas();  // CTAs per weight-gradient kernel when they run under the next step's chain passes (0 = off)
 void op_wgrad2_tc_multi(Ctx& c, const Wgrad2TcSpec* specs, int n);  // one reduction launch for up to three gradients
 
+// The affine coupling folded into the col2im that finishes the block's last contraction (north_star: "the affine
+// coupling (sigmoid scale, shift, log|s| sum) ... fused into the conv epilogues"): the kernel that gathers the tap
+// (row) sums of P into (logS, T) applies sigma / S.X1 + T / sum log S (forward), the inverse, or the whole backward
+// of invertible_layer_glow.jl:142-151 to the transformed half in place, so the block output never reaches HBM.
+struct CouplingFuse {
+  int mode;               // 0: Y1 = S.X1 + T (+ logdet)   1: X1 = (Y1 - T) / (S + eps)   2: backward (X1, dX1, dY3)
+  int C1;                 // channels of the transformed half; the block has 2*C1 outputs (logS | T)
+  float* a1; long long a1_bs;   // X1 -> Y1 (mode 0), Y1 -> X1 (modes 1, 2), in place
+  float* d1; long long d1_bs;   // mode 2: dY1 -> dX1 in place
+  float* dY3;             // mode 2: masked gradient of the block output (B, 2*C1, px), compact
+  float low, high, invB;  // SigmoidLayer bounds; 1/B of the logdet terms (0 without logdet)
+  double* ld;             // mode 0: logdet accumulator (nullable)
+  unsigned* amax;         // mode 2: bits of max|dY3| (nullable)
+  bool done;              // set by op_rb_chain when the fused kernel ran (the caller then skips op_coupling_*)
+};
+
 // Fused pass of the block's three contractions (conv_tc_chain.cu): im2col-GEMM -> per-pixel GEMM ->
 // tap-expanded GEMM + col2im.  mode 0 = forward (bias + ReLU epilogues), mode 1 = backward (relu-grad masks).
 struct ChainSpec {
@@ -117,6 +133,7 @@ struct ChainSpec {
   float* out1; long long out1_bs; int out1_accum;
   const float* add; long long add_bs; int add_n;
   const uint32_t* smax = nullptr;  // INB_PREC_FP16X3 backward pass: the scale of `in` (col2im divides by it)
+  CouplingFuse* fuse = nullptr;    // fold the affine coupling into the col2im (out0 etc. are then unused)
 };
 int chain_n3pad(int taps, int Cn);
 inline int chain_nh_pad(int nh) { return nh <= 128 ? 128 : 256; }  // hidden width the chain kernels run at

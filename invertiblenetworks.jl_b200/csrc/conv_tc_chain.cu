@@ -1622,6 +1622,117 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
   }
 }
 
+// col2im + affine coupling (CouplingFuse) in two phases per block of 32 pixels.  Phase 1 is k_col2im_g: thread =
+// (pixel, group of 4 output channels), 16-byte loads of the tap (row) sums, the same order of additions (bit-identical
+// Y3), results into a [Cn][32 + 1] shared-memory tile.  Phase 2 walks (channel of the transformed half, pixel) with the
+// warp's 32 lanes on 32 consecutive pixels, so every access to X1 / Y1 / dY1 / dY3 is one full 128-byte line.
+// (A first version that kept the (pixel, channel pair) mapping for both phases was as slow as the two kernels it
+// replaced: its plane accesses covered ~11 pixels per warp instruction.)  J = C1 / 2 = Cn / 4 groups per pixel.
+__device__ __forceinline__ float cf_sigmoid(float x, float low, float high) { return low + (high - low) / (1.f + expf(-x)); }
+template <int J, int MODE>
+__global__ void __launch_bounds__(32 * J) k_col2im_coupling(const Col2imArgs a, const CouplingFuse f) {
+  constexpr int CN = 4 * J;
+  __shared__ float tile[CN][33];
+  __shared__ float red[32];
+  const int pl = threadIdx.x / J, g = threadIdx.x % J;
+  const int pix0 = (int)(blockIdx.x * 32);
+  const int pix = pix0 + pl;
+  const long long b = blockIdx.y;
+  if (pix < (int)a.px) {
+    const long long m = b * a.px + pix;
+    const int x = pix % a.W;
+    const int yz = pix / a.W;
+    const int y = yz % a.H;
+    const int z = yz / a.H;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.qsum && a.D == 1 && a.taps == 3) {
+      const float* row = a.P + m * a.n3pad + 4 * g;
+      const long long rs = (long long)a.W * a.n3pad;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 w0 = (y > 0) ? __ldg(reinterpret_cast<const float4*>(row - rs)) : zero;
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(row + a.cstride));
+      const float4 w2 = (y + 1 < a.H) ? __ldg(reinterpret_cast<const float4*>(row + rs + 2 * a.cstride)) : zero;
+      acc.x = (w0.x + w1.x) + w2.x; acc.y = (w0.y + w1.y) + w2.y;
+      acc.z = (w0.z + w1.z) + w2.z; acc.w = (w0.w + w1.w) + w2.w;
+    } else {
+      for (int tap = 0; tap < a.taps; ++tap) {
+        int dx, dy, dz;
+        if (a.qsum) { dx = 0; dy = tap % 3 - 1; dz = (a.D > 1) ? tap / 3 - 1 : 0; }
+        else chain_tap_offset(tap, a.ksz, a.D, dx, dy, dz);
+        const int xx = x + dx, yy = y + dy, zz = z + dz;
+        if (xx < 0 || xx >= a.W || yy < 0 || yy >= a.H || zz < 0 || zz >= a.D) continue;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(
+            a.P + (m + dx + (long long)dy * a.W + (long long)dz * a.W * a.H) * a.n3pad + tap * a.cstride + 4 * g));
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+      }
+    }
+    const float osc = col2im_scale(a);
+    tile[4 * g][pl] = acc.x * osc;
+    tile[4 * g + 1][pl] = acc.y * osc;
+    tile[4 * g + 2][pl] = acc.z * osc;
+    tile[4 * g + 3][pl] = acc.w * osc;
+  }
+  __syncthreads();
+  float lsum = 0.f, gmax = 0.f;
+  const int C1 = 2 * J;
+  for (int i = threadIdx.x; i < C1 * 32; i += 32 * J) {
+    const int ch = i >> 5, p2 = i & 31;
+    const int px2 = pix0 + p2;
+    if (px2 >= (int)a.px) continue;
+    const float lsv = tile[ch][p2], tvv = tile[C1 + ch][p2];
+    float* ap = f.a1 + b * f.a1_bs + (long long)ch * a.px + px2;
+    const float S = cf_sigmoid(fmaxf(lsv, 0.f), f.low, f.high);  // RB output ReLU (layer_residual_block.jl:133)
+    const float T = fmaxf(tvv, 0.f);
+    if (MODE == 0) {
+      *ap = S * *ap + T;                 // invertible_layer_glow.jl:112
+      lsum += logf(fabsf(S));            // :210
+    } else if (MODE == 1) {
+      *ap = (*ap - T) / (S + 1.1920929e-07f);  // :127, eps(Float32)
+    } else {
+      float* dp = f.d1 + b * f.d1_bs + (long long)ch * a.px + px2;
+      const float dyv = *dp;
+      const float X1 = (*ap - T) / (S + 1.1920929e-07f);
+      float dS = dyv * X1;               // :144
+      dS -= f.invB / S;                  // :145-147, 211
+      *ap = X1;
+      *dp = dyv * S;                     // :149
+      const float e = (f.high - S) / (S - f.low);  // activation_functions.jl:213-217 through the logit
+      const float dl = (f.high - f.low) * dS * e / ((1.f + e) * (1.f + e));
+      const float gl = (lsv < 0.f) ? 0.f : dl;  // _relugrad of the block's output ReLU (:84)
+      const float gt = (tvv < 0.f) ? 0.f : dyv; // dT = dY1 (:143)
+      f.dY3[(b * 2 * C1 + ch) * a.px + px2] = gl;
+      f.dY3[(b * 2 * C1 + C1 + ch) * a.px + px2] = gt;
+      gmax = fmaxf(gmax, fmaxf(fabsf(gl), fabsf(gt)));
+    }
+  }
+  if (MODE == 0 && f.ld) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 0.0;
+      for (int w = 0; w < J; ++w) r += (double)red[w];
+      atomicAdd(f.ld, r * (double)f.invB);
+    }
+  }
+  if (MODE == 2 && f.amax) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+    if ((threadIdx.x & 31) == 0 && gmax > 0.f) atomicMax(f.amax, __float_as_uint(gmax));
+  }
+}
+template <int J>
+static void launch_col2im_coupling(cudaStream_t st, const dim3& grid, const Col2imArgs& ca, const CouplingFuse& f) {
+  if (f.mode == 0) k_col2im_coupling<J, 0><<<grid, 32 * J, 0, st>>>(ca, f);
+  else if (f.mode == 1) k_col2im_coupling<J, 1><<<grid, 32 * J, 0, st>>>(ca, f);
+  else k_col2im_coupling<J, 2><<<grid, 32 * J, 0, st>>>(ca, f);
+}
+static bool col2im_coupling_enabled() {
+  static const bool on = [] { const char* e = getenv("INB_FUSE_COUPLING"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // ---------------------------------------------------------------- weight packing for one chain pass
 // One launch packs the three operands of a pass into bf16 hi/lo planes:
 //   w1 [nh][kp]     dense-K rows against the im2col operand:  column tap*C1 + c  <-  wa[n][c][T-1-tap]   (NNlib conv)
@@ -1938,6 +2049,34 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     ca.add = s.add; ca.add_bs = s.add_bs; ca.add_n = s.add_n;
     ca.oscale = f16 ? 1.f / kF16WScale : 1.f;
     ca.smax = f16 ? s.smax : nullptr;
+    if (s.fuse) s.fuse->done = false;
+    if (s.fuse && col2im_coupling_enabled() && s.Cn == 2 * s.fuse->C1 && s.fuse->C1 % 2 == 0 && !s.out1 && !s.add &&
+        ca.cstride % 4 == 0 && ca.n3pad % 4 == 0 && s.Cn % 4 == 0 && s.B <= 65535 && s.g.px < (1ll << 31)) {
+      const int J = s.fuse->C1 / 2;
+      const dim3 grid((unsigned)cdiv(s.g.px, 32), (unsigned)s.B, 1);
+      // bytes: the P rows, the transformed half read + written (twice in the backward), dY3 written in the backward
+      const double elems = (double)a.M * s.fuse->C1;
+      Prof pf(c, s.fuse->mode == 2 ? F_COUPLING_BWD : (s.fuse->mode == 1 ? F_COUPLING_INV : F_COUPLING_FWD), 1, 0,
+              4.0 * ca.n3pad * a.M + (s.fuse->mode == 2 ? 24.0 : 8.0) * elems);
+      bool ok = true;
+      switch (J) {
+        case 1: launch_col2im_coupling<1>(c.st, grid, ca, *s.fuse); break;
+        case 2: launch_col2im_coupling<2>(c.st, grid, ca, *s.fuse); break;
+        case 3: launch_col2im_coupling<3>(c.st, grid, ca, *s.fuse); break;
+        case 4: launch_col2im_coupling<4>(c.st, grid, ca, *s.fuse); break;
+        case 6: launch_col2im_coupling<6>(c.st, grid, ca, *s.fuse); break;
+        case 8: launch_col2im_coupling<8>(c.st, grid, ca, *s.fuse); break;
+        case 12: launch_col2im_coupling<12>(c.st, grid, ca, *s.fuse); break;
+        case 16: launch_col2im_coupling<16>(c.st, grid, ca, *s.fuse); break;
+        case 24: launch_col2im_coupling<24>(c.st, grid, ca, *s.fuse); break;
+        default: ok = false;
+      }
+      if (ok) {
+        INB_CUDA(cudaGetLastError());
+        s.fuse->done = true;
+        return;
+      }
+    }
     Prof pf(c, F_COL2IM, 1, 0, (4.0 * ca.n3pad + 4.0 * s.Cn) * a.M);
     const unsigned nb = (unsigned)cdiv(a.M, 128);
     const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;

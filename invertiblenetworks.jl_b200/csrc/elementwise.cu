@@ -102,6 +102,58 @@ __global__ void k_squeeze(const float* __restrict__ src, long long sbs, float* _
   }
 }
 
+// The same map with four full-resolution x per thread: one 16-byte access on the full-resolution side, two 8-byte
+// accesses on the squeezed side, and 32-bit index arithmetic inside a (sample, channel) plane (grid.y walks the planes).
+// The two-elements-per-thread kernel above is bound by its 64-bit division chain (1.4 TB/s); this one by HBM.
+template <bool FWD>
+__global__ void __launch_bounds__(256)
+k_squeeze4(const float* __restrict__ src, long long sbs, float* __restrict__ dst, long long dbs, int C, int W, int H,
+           int D, int planes) {
+  const unsigned Wq = (unsigned)W >> 2, Wh = (unsigned)W >> 1, Hh = (unsigned)H >> 1;
+  const unsigned nq = Wq * (unsigned)H * (unsigned)D;  // quads per plane
+  const long long pxf = (long long)W * H * D;
+  const long long pxh = pxf >> ((D > 1) ? 3 : 2);
+  for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+    const int b = pl / C, c = pl - b * C;
+    const float* fs = (FWD ? src + b * sbs : dst + b * dbs) + (long long)c * pxf;
+    const float* hsb = FWD ? dst + b * dbs : src + b * sbs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+      const unsigned row = i / Wq, xq = i - row * Wq;   // row = z * H + y
+      const unsigned z = row / (unsigned)H, y = row - z * (unsigned)H;
+      const unsigned p0 = 2 * (y & 1) + 4 * (z & 1);
+      const long long half = ((long long)(z >> 1) * Hh + (y >> 1)) * Wh + 2 * xq;
+      float* h0 = const_cast<float*>(hsb) + ((long long)p0 * C + c) * pxh + half;
+      float* h1 = h0 + (long long)C * pxh;
+      float* f = const_cast<float*>(fs) + (long long)row * W + 4 * xq;
+      if (FWD) {
+        const float4 v = *reinterpret_cast<const float4*>(f);
+        *reinterpret_cast<float2*>(h0) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2*>(h1) = make_float2(v.y, v.w);
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(h0), bq = *reinterpret_cast<const float2*>(h1);
+        *reinterpret_cast<float4*>(f) = make_float4(a.x, bq.x, a.y, bq.y);
+      }
+    }
+  }
+}
+template <bool FWD>
+static bool launch_squeeze4(Ctx& c, const Geo& g, int B, int C, View full, View half) {
+  const long long pxh = g.px >> (g.nd == 3 ? 3 : 2);
+  const bool ok = g.W % 4 == 0 && full.bs % 4 == 0 && ((uintptr_t)full.p & 15) == 0 && half.bs % 2 == 0 &&
+                  ((uintptr_t)half.p & 7) == 0 && pxh % 2 == 0 && g.px / 4 < (1ll << 31) && (long long)B * C < (1ll << 31);
+  if (!ok) return false;
+  const unsigned nq = (unsigned)(g.px / 4);
+  const int planes = B * C;
+  // ~4 blocks per SM in flight over the whole launch
+  unsigned gx = (nq + 255) / 256;
+  const unsigned want = (unsigned)std::max<long long>(1, cdiv(148LL * 8, planes));
+  if (gx > want) gx = want;
+  const dim3 grid(gx, (unsigned)std::min(planes, 65535), 1);
+  if (FWD) k_squeeze4<true><<<grid, 256, 0, c.st>>>(full.p, full.bs, half.p, half.bs, C, g.W, g.H, g.D, planes);
+  else k_squeeze4<false><<<grid, 256, 0, c.st>>>(half.p, half.bs, full.p, full.bs, C, g.W, g.H, g.D, planes);
+  return true;
+}
+
 static int grid_for(long long total, int block, int per_sm = 8) {
   long long g = cdiv(total, block);
   long long cap = 148LL * per_sm;
@@ -114,14 +166,16 @@ void op_squeeze(Ctx& c, const Geo& g, int B, int C, View in, View out) {
   if (c.dry()) return;
   Prof pf(c, F_SQUEEZE, 1, 0, 8.0 * B * C * g.px);
   long long total = (long long)B * C * g.D * g.H * (g.W / 2);
-  k_squeeze<true><<<grid_for(total, 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, g.D, B);
+  if (!launch_squeeze4<true>(c, g, B, C, in, out))
+    k_squeeze<true><<<grid_for(total, 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, g.D, B);
   INB_CUDA(cudaGetLastError());
 }
 void op_unsqueeze(Ctx& c, const Geo& g, int B, int C, View in, View out) {
   if (c.dry()) return;
   Prof pf(c, F_SQUEEZE, 1, 0, 8.0 * B * C * g.px);
   long long total = (long long)B * C * g.D * g.H * (g.W / 2);
-  k_squeeze<false><<<grid_for(total, 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, g.D, B);
+  if (!launch_squeeze4<false>(c, g, B, C, out, in))
+    k_squeeze<false><<<grid_for(total, 256), 256, 0, c.st>>>(in.p, in.bs, out.p, out.bs, C, g.W, g.H, g.D, B);
   INB_CUDA(cudaGetLastError());
 }
 
@@ -395,28 +449,29 @@ k_an_hh_fwd(const float* __restrict__ x, long long xbs, float* __restrict__ y, l
     for (int i = 0; i < C; ++i) acc += logf(fabsf(sm.s[i]));
     atomicAdd(ld, (double)((float)px * acc));  // actnorm.jl:188-189
   }
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= total) return;
+  // persistent blocks (one wave of resident CTAs, grid-stride): no partial last wave, parameters staged once per CTA
   const long long pxv = px / V;
-  const long long bi = g / pxv, pix = (g - bi * pxv) * V;
-  const float* xp = x + bi * xbs + pix;
-  float a[C][V];
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long bi = g / pxv, pix = (g - bi * pxv) * V;
+    const float* xp = x + bi * xbs + pix;
+    float a[C][V];
 #pragma unroll
-  for (int ch = 0; ch < C; ++ch) ldv<V>(xp + ch * px, a[ch]);
-  if (s) {
+    for (int ch = 0; ch < C; ++ch) ldv<V>(xp + ch * px, a[ch]);
+    if (s) {
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch)
+      for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-      for (int u = 0; u < V; ++u) a[ch][u] = a[ch][u] * sm.s[ch] + sm.b[ch];
+        for (int u = 0; u < V; ++u) a[ch][u] = a[ch][u] * sm.s[ch] + sm.b[ch];
+    }
+    if (v1) {
+      reflect<C, V>(a, sm.v[0], sm.n[0]);
+      reflect<C, V>(a, sm.v[1], sm.n[1]);
+      reflect<C, V>(a, sm.v[2], sm.n[2]);
+    }
+    float* yp = y + bi * ybs + pix;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) stv<V>(yp + ch * px, a[ch]);
   }
-  if (v1) {
-    reflect<C, V>(a, sm.v[0], sm.n[0]);
-    reflect<C, V>(a, sm.v[1], sm.n[1]);
-    reflect<C, V>(a, sm.v[2], sm.n[2]);
-  }
-  float* yp = y + bi * ybs + pix;
-#pragma unroll
-  for (int ch = 0; ch < C; ++ch) stv<V>(yp + ch * px, a[ch]);
 }
 
 template <int C, int V>
@@ -426,28 +481,28 @@ k_hh_an_inv(const float* __restrict__ y, long long ybs, float* __restrict__ x, l
             const float* __restrict__ v2, const float* __restrict__ v3, long long px, long long total) {
   __shared__ HhSmem<C> sm;
   load_hh_smem<C>(sm, s, b, v1, v2, v3);
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (g >= total) return;
   const long long pxv = px / V;
-  const long long bi = g / pxv, pix = (g - bi * pxv) * V;
-  const float* yp = y + bi * ybs + pix;
-  float a[C][V];
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long bi = g / pxv, pix = (g - bi * pxv) * V;
+    const float* yp = y + bi * ybs + pix;
+    float a[C][V];
 #pragma unroll
-  for (int ch = 0; ch < C; ++ch) ldv<V>(yp + ch * px, a[ch]);
-  if (v1) {
-    reflect<C, V>(a, sm.v[2], sm.n[2]);
-    reflect<C, V>(a, sm.v[1], sm.n[1]);
-    reflect<C, V>(a, sm.v[0], sm.n[0]);
+    for (int ch = 0; ch < C; ++ch) ldv<V>(yp + ch * px, a[ch]);
+    if (v1) {
+      reflect<C, V>(a, sm.v[2], sm.n[2]);
+      reflect<C, V>(a, sm.v[1], sm.n[1]);
+      reflect<C, V>(a, sm.v[0], sm.n[0]);
+    }
+    if (s) {
+#pragma unroll
+      for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+        for (int u = 0; u < V; ++u) a[ch][u] = (a[ch][u] - sm.b[ch]) / sm.s[ch];  // actnorm.jl:93
+    }
+    float* xp = x + bi * xbs + pix;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) stv<V>(xp + ch * px, a[ch]);
   }
-  if (s) {
-#pragma unroll
-    for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-      for (int u = 0; u < V; ++u) a[ch][u] = (a[ch][u] - sm.b[ch]) / sm.s[ch];  // actnorm.jl:93
-  }
-  float* xp = x + bi * xbs + pix;
-#pragma unroll
-  for (int ch = 0; ch < C; ++ch) stv<V>(xp + ch * px, a[ch]);
 }
 
 // ---------------------------------------------------------------- backward of both
@@ -792,17 +847,31 @@ static int pick_vec(int C, long long px, std::initializer_list<const View*> vs) 
   return v;
 }
 
+// one wave of resident CTAs for a grid-stride kernel of 256 threads (occupancy queried once per instantiation)
+template <class K>
+static int persistent_grid(K kern, long long blocks) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 2;
+  }
+  const long long cap = 148LL * per_sm;
+  return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+#define INB_PGRID(KERN) ([&] { static int per = 0; if (!per) per = persistent_grid(KERN, 1LL << 40) / 148; \
+                               return (int)std::max<long long>(1, std::min<long long>(nblk, 148LL * per)); }())
+
 void op_an_hh_fwd(Ctx& c, long long px, int B, int C, View x, View y, const float* s, const float* b,
                   const float* v1, const float* v2, const float* v3, double* ld) {
   if (c.dry()) return;
   Prof pf(c, F_AN_HH_FWD, 1, 12.0 * B * C * px, 8.0 * B * C * px);
   int V = pick_vec(C, px, {&x, &y});
   long long total = px / V * B;
-  int grid = (int)cdiv(total, 256);
+  const long long nblk = cdiv(total, 256);
 #define L_(CC)                                                                                       \
-  if (V == 4) k_an_hh_fwd<CC, (CC <= 12 ? 4 : 1)><<<grid, 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld); \
-  else if (V == 2) k_an_hh_fwd<CC, (CC <= 24 ? 2 : 1)><<<grid, 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld); \
-  else k_an_hh_fwd<CC, 1><<<grid, 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld);
+  if (V == 4) { auto k = k_an_hh_fwd<CC, (CC <= 12 ? 4 : 1)>; k<<<INB_PGRID(k), 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld); } \
+  else if (V == 2) { auto k = k_an_hh_fwd<CC, (CC <= 24 ? 2 : 1)>; k<<<INB_PGRID(k), 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld); } \
+  else { auto k = k_an_hh_fwd<CC, 1>; k<<<INB_PGRID(k), 256, 0, c.st>>>(x.p, x.bs, y.p, y.bs, s, b, v1, v2, v3, px, total, ld); }
   INB_FOR_C(C, L_)
 #undef L_
   INB_CUDA(cudaGetLastError());
@@ -814,11 +883,11 @@ void op_hh_an_inv(Ctx& c, long long px, int B, int C, View y, View x, const floa
   Prof pf(c, F_HH_AN_INV, 1, 12.0 * B * C * px, 8.0 * B * C * px);
   int V = pick_vec(C, px, {&x, &y});
   long long total = px / V * B;
-  int grid = (int)cdiv(total, 256);
+  const long long nblk = cdiv(total, 256);
 #define L_(CC)                                                                                       \
-  if (V == 4) k_hh_an_inv<CC, (CC <= 12 ? 4 : 1)><<<grid, 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total); \
-  else if (V == 2) k_hh_an_inv<CC, (CC <= 24 ? 2 : 1)><<<grid, 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total); \
-  else k_hh_an_inv<CC, 1><<<grid, 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total);
+  if (V == 4) { auto k = k_hh_an_inv<CC, (CC <= 12 ? 4 : 1)>; k<<<INB_PGRID(k), 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total); } \
+  else if (V == 2) { auto k = k_hh_an_inv<CC, (CC <= 24 ? 2 : 1)>; k<<<INB_PGRID(k), 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total); } \
+  else { auto k = k_hh_an_inv<CC, 1>; k<<<INB_PGRID(k), 256, 0, c.st>>>(y.p, y.bs, x.p, x.bs, s, b, v1, v2, v3, px, total); }
   INB_FOR_C(C, L_)
 #undef L_
   INB_CUDA(cudaGetLastError());

@@ -43,6 +43,8 @@ struct RBHidden {
   // INB_PREC_FP16X3: device word with the bits of max|dY3|, when the producer of dY3 already reduced it (the coupling
   // backward kernel does); rb_backward computes it with a pass over dY3 otherwise
   uint32_t* dy_absmax = nullptr;
+  // request to fold the affine coupling into the block's last kernel (rb_forward sets fuse->done when it did)
+  CouplingFuse* fuse = nullptr;
 };
 
 // layer_residual_block.jl:119-134, output = PRE-activation Y3 (B, Cout, px) compact; the consumers

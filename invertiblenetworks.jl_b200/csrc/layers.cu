@@ -245,6 +245,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     cs.P = c.ar->f32((size_t)M * n3pad);
     cs.out0 = Y3; cs.out0_bs = (long long)s.Cout * px; cs.n0 = s.Cout;
     cs.add_n = 1 << 30;
+    cs.fuse = h.fuse;
     op_rb_chain(c, cs);
     c.ar->release(m);
     return;
@@ -414,8 +415,10 @@ void flow_forward(Ctx& c, const FlowShape& f, View x, View y, View cond, const F
   h.Y2 = c.ar->f32(rb_hidden_elems(rs));
   h.G = nullptr;
   float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
+  CouplingFuse cf{0, C1, y.p, y.bs, nullptr, 0, nullptr, f.low, f.high, 1.f / (float)f.B, f.logdet ? ld : nullptr, nullptr, false};
+  h.fuse = &cf;
   rb_forward(c, rs, sub(y, C1, px), cond, p.rb, h, Y3);  // glow.jl:109, X2 = second part
-  op_coupling_fwd(c, px, f.B, C1, y, y, Y3, f.low, f.high, f.logdet ? ld : nullptr);  // :110-116
+  if (!cf.done) op_coupling_fwd(c, px, f.B, C1, y, y, Y3, f.low, f.high, f.logdet ? ld : nullptr);  // :110-116
   c.ar->release(m);
 }
 
@@ -429,8 +432,10 @@ void flow_inverse(Ctx& c, const FlowShape& f, View y, View x, View cond, const F
   h.Y2 = c.ar->f32(rb_hidden_elems(rs));
   h.G = nullptr;
   float* Y3 = c.ar->f32((size_t)f.B * rs.Cout * px);
+  CouplingFuse cf{1, C1, y.p, y.bs, nullptr, 0, nullptr, f.low, f.high, 0.f, nullptr, nullptr, false};
+  h.fuse = &cf;
   rb_forward(c, rs, sub(y, C1, px), cond, p.rb, h, Y3);             // glow.jl:124
-  op_coupling_inv(c, px, f.B, C1, y, y, Y3, f.low, f.high);        // :127
+  if (!cf.done) op_coupling_inv(c, px, f.B, C1, y, y, Y3, f.low, f.high);        // :127
   op_hh_an_inv(c, px, f.B, f.C, y, x, p.s, p.b, p.v1, p.v2, p.v3); // :130, actnorm.jl:93
   c.ar->release(m);
 }
@@ -459,13 +464,18 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
   View y2 = sub(y, C1, px), dy2 = sub(dy, C1, px);
   // recompute the block once (glow.jl:139 -> :124; the reference recomputes it again at
   // layer_residual_block.jl:143 - same values)
-  rb_forward(c, rs, y2, cond, p.rb, h, Y3);
-  // X1, dX1, and the masked gradient of the block output        glow.jl:127,142-151
   if (prec_f16(c.prec)) {  // max|dY3| falls out of the kernel that writes dY3
     h.dy_absmax = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes(256));
     op_zero(c, h.dy_absmax, 4);
   }
-  op_coupling_bwd(c, px, f.B, C1, y, y, dy, dy, Y3, f.low, f.high, f.logdet, h.dy_absmax);
+  // X1, dX1, and the masked gradient of the block output        glow.jl:127,142-151 - folded into the block's last
+  // kernel on the fused tensor-core chain, a kernel of its own otherwise
+  CouplingFuse cf{2, C1, y.p, y.bs, dy.p, dy.bs, Y3, f.low, f.high, f.logdet ? 1.f / (float)f.B : 0.f, nullptr,
+                  h.dy_absmax, false};
+  h.fuse = &cf;
+  rb_forward(c, rs, y2, cond, p.rb, h, Y3);
+  h.fuse = nullptr;
+  if (!cf.done) op_coupling_bwd(c, px, f.B, C1, y, y, dy, dy, Y3, f.low, f.high, f.logdet, h.dy_absmax);
   // dX2 = RB.backward(...) + dY2                                 glow.jl:151
   rb_backward(c, rs, Y3, y2, cond, p.rb, h, g.rb, dy2, dy2.p, dy2.bs, dcond);
   // Conv1x1 inverse on (dX_, X_) + ActNorm backward              glow.jl:159, actnorm.jl:100-123
