@@ -23,6 +23,8 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["gb"]
     prec = sys.argv[3] if len(sys.argv) > 3 else cfg["precision"]
     nsteps = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    if len(sys.argv) > 5:  # flow steps per scale (a K = 1 network has every kernel of the step in ~40 launches)
+        cfg = dict(cfg, K=int(sys.argv[5]))
     dev = torch.device("cuda", 0)
     W = bench.Workload(cfg, prec, B, 0, dev)
     for _ in range(3):
