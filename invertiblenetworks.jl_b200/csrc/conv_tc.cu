@@ -111,6 +111,21 @@ CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows
   return m;
 }
 
+// fp32 planes [nplanes][rows][cols], box (cols, box_rows, 1), no swizzle: the tap-row planes of the fused chain's Pq (a
+// ragged last tile is clipped at `rows`, so it cannot spill into the next plane)
+CUtensorMap make_planes_map_f32_dense(const float* base, int cols, long long rows, int nplanes, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)nplanes};
+  cuuint64_t str[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(2, "cuTensorMapEncodeTiled(dense fp32 planes) failed with %d", (int)r);
+  return m;
+}
+
 TileBox make_tile_box(const Geo& g, int B, int P) {
   TileBox t{1, 1, 1, 1, false};
   int rem = P;

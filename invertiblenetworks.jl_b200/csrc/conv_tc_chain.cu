@@ -50,6 +50,7 @@ struct ChainArgs {
   // taps*Cn to (taps/3)*cq columns per pixel (Pq[m][tg*cq + n], cq = Cn rounded up to 4, pitch nq = (taps/3)*cq)
   int qsum, Cn, cq, nq, ntg;
   int pstag_bytes;        // k_rb_chain2: size of the P staging area
+  int hints;              // k_rb_chain2 L2 eviction hints of the bulk stores: 1 hidden planes evict_first, 2 P / Pq evict_last
   int npiece, n3piece;    // k_rb_chain2: GEMM3 runs in npiece passes of n3piece (<= 256) columns through the same TMEM region
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
   float wsinv;            // accumulators of GEMM1 / GEMM2 are multiplied by this before the epilogue's bias / mask:
@@ -1267,12 +1268,19 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
           }
           acc = make_float4(t4[0], t4[1], t4[2], t4[3]);
         }
-        *reinterpret_cast<float4*>(qst + r * a.nq + tg * a.cq + 4 * g) = acc;
+        *reinterpret_cast<float4*>(qst + (tg * 128 + r) * a.cq + 4 * g) = acc;  // [tap row][pixel][cq]
       }
       fence_proxy_async();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
       if (tid == 0) {
-        tma_store_2d(&maps.P, qst, 0, ptile * 128);
+        // one dense [128][cq] box per tap row into that row's PLANE of Pq: the col2im gather then reads every plane as
+        // contiguous pixels x cq floats (no sector shared with a segment another pixel row wants)
+        if (a.hints & 2) {
+          const uint64_t pol = l2_policy_evict_last();
+          for (int tg = 0; tg < a.ntg; ++tg) tma_store_3d_hint(&maps.P, qst + tg * 128 * a.cq, 0, ptile * 128, tg, pol);
+        } else {
+          for (int tg = 0; tg < a.ntg; ++tg) tma_store_3d(&maps.P, qst + tg * 128 * a.cq, 0, ptile * 128, tg);
+        }
         bulk_commit();
       }
     };
@@ -1455,6 +1463,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
     // ------------------------------------------------------------ TMA store warp: hidden chunks -> HBM
     if (lane == 0) {
       uint32_t cs = 0;
+      const uint64_t pol = l2_policy_evict_first();
       for (int tp = pair0; tp < npairs; tp += pstride) {
         const int tile = 2 * tp + (int)rank;
         for (int stg = 0; stg < 2; ++stg) {
@@ -1463,8 +1472,12 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             mbar_wait(sready + slot, (cs / kChain2Slots) & 1);
             if (!(a.exp & 4)) {
 #pragma unroll
-              for (int pl = 0; pl < NP; ++pl)
-                tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+              for (int pl = 0; pl < NP; ++pl) {
+                if (a.hints & 1)
+                  tma_store_2d_hint(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128, pol);
+                else
+                  tma_store_2d(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128);
+              }
             }
             bulk_commit();
             if (cs > 0) {  // one store stays in flight; the one before it has read its slot
@@ -1491,8 +1504,11 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
 // out[b][n][pix] = sum_tap P[pix + off(tap)][tap*Cn + n]  (+ passthrough add), coalesced both ways through a
 // shared-memory transpose: phase 1 walks (pixel, n) with n fastest (contiguous in P), phase 2 walks pixels.
 struct Col2imArgs {
-  int qsum;  // P holds tap-ROW sums (k_rb_chain2 with qsum): `taps` counts tap rows, column = row * cstride + n
-  int cstride;
+  // element (pixel row m, tap t, channel n) of P sits at P[m * n3pad + t * cstride + n].  Full P: n3pad = the padded row,
+  // cstride = Cn.  qsum (k_rb_chain2's tap-ROW sums): `taps` counts tap rows and every tap row is a dense PLANE
+  // [M][cq] of its own: n3pad = cq, cstride = M * cq.
+  int qsum;
+  long long cstride;
   int W, H, D, ksz, taps, Cn, n3pad;
   long long px, M;
   const float* P;
@@ -1986,7 +2002,9 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
       mp.O2[pl] = mp.W2[pl];
     }
   }
-  mp.P = a.qsum ? make_rows_map_f32_dense(s.P, a.nq, a.M, a.nq, 128) : make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
+  mp.P = a.qsum ? make_planes_map_f32_dense(s.P, a.cq, a.M, a.ntg, 128) : make_rows_map_f32(s.P, a.n3pad, a.M, 32, 128);
+  static const int l2_hints = [] { const char* e = getenv("INB_L2_HINTS"); return e ? atoi(e) : 0; }();
+  a.hints = l2_hints;
   unsigned grid = (unsigned)std::min(a.ntiles, 148);
   const double flops = 2.0 * a.M * ((double)s.in.pitch * s.nh + (double)s.nh * s.nh + (double)s.nh * a.n3pad) * NT;
   {
@@ -2042,13 +2060,14 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     Col2imArgs ca{};
     ca.W = s.g.W; ca.H = s.g.H; ca.D = s.g.D; ca.ksz = s.k1; ca.taps = taps; ca.Cn = s.Cn; ca.n3pad = a.n3pad;
     ca.qsum = a.qsum; ca.cstride = s.Cn;
-    if (a.qsum) { ca.taps = a.ntg; ca.n3pad = a.nq; ca.cstride = a.cq; }
+    if (a.qsum) { ca.taps = a.ntg; ca.n3pad = a.cq; ca.cstride = a.M * a.cq; }
     ca.px = s.g.px; ca.M = a.M; ca.P = s.P;
     ca.out0 = s.out0; ca.out0_bs = s.out0_bs; ca.n0 = s.n0;
     ca.out1 = s.out1; ca.out1_bs = s.out1_bs; ca.out1_accum = s.out1_accum;
     ca.add = s.add; ca.add_bs = s.add_bs; ca.add_n = s.add_n;
     ca.oscale = f16 ? 1.f / kF16WScale : 1.f;
     ca.smax = f16 ? s.smax : nullptr;
+    const int prow = a.qsum ? a.nq : a.n3pad;  // floats of P per pixel (byte accounting)
     if (s.fuse) s.fuse->done = false;
     if (s.fuse && col2im_coupling_enabled() && s.Cn == 2 * s.fuse->C1 && s.fuse->C1 % 2 == 0 && !s.out1 && !s.add &&
         ca.cstride % 4 == 0 && ca.n3pad % 4 == 0 && s.Cn % 4 == 0 && s.B <= 65535 && s.g.px < (1ll << 31)) {
@@ -2057,7 +2076,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
       // bytes: the P rows, the transformed half read + written (twice in the backward), dY3 written in the backward
       const double elems = (double)a.M * s.fuse->C1;
       Prof pf(c, s.fuse->mode == 2 ? F_COUPLING_BWD : (s.fuse->mode == 1 ? F_COUPLING_INV : F_COUPLING_FWD), 1, 0,
-              4.0 * ca.n3pad * a.M + (s.fuse->mode == 2 ? 24.0 : 8.0) * elems);
+              4.0 * prow * a.M + (s.fuse->mode == 2 ? 24.0 : 8.0) * elems);
       bool ok = true;
       switch (J) {
         case 1: launch_col2im_coupling<1>(c.st, grid, ca, *s.fuse); break;
@@ -2077,7 +2096,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
         return;
       }
     }
-    Prof pf(c, F_COL2IM, 1, 0, (4.0 * ca.n3pad + 4.0 * s.Cn) * a.M);
+    Prof pf(c, F_COL2IM, 1, 0, (4.0 * prow + 4.0 * s.Cn) * a.M);
     const unsigned nb = (unsigned)cdiv(a.M, 128);
     const bool v4 = s.Cn % 4 == 0 && ca.cstride % 4 == 0 && ca.n3pad % 4 == 0;
     const bool v2 = s.Cn % 2 == 0 && ca.cstride % 2 == 0 && ca.n3pad % 2 == 0;

@@ -12,4 +12,6 @@ CUtensorMap make_w_map(const __nv_bfloat16* base, int ktot, int rows, int ck);
 CUtensorMap make_rows_map(const __nv_bfloat16* base, int pitch, long long rows, int box_c, int box_rows);
 CUtensorMap make_rows_map_f32(const float* base, int pitch, long long rows, int box_c, int box_rows);
 CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows, int box_c, int box_rows);
+// fp32 planes [nplanes][rows][cols] (dense, cols * 4 a multiple of 16), box (cols, box_rows, 1), no swizzle
+CUtensorMap make_planes_map_f32_dense(const float* base, int cols, long long rows, int nplanes, int box_rows);
 }  // namespace inb
