@@ -41,16 +41,16 @@ CONFIGS = {
     "cfg2": dict(kind="glow", n_in=3, nh=256, L=3, K=16, sp=(256, 256), gb=64, precision="fp16x3",
                  label="NetworkGlow(3,256,L=3,K=16;split_scales=true) on 256x256x3"),
     # BASELINE configs[0] (examples/networks/network_glow.jl:20-26)
-    "cfg1": dict(kind="glow", n_in=1, nh=32, L=2, K=2, sp=(64, 64), gb=8, precision="fp32",
+    "cfg1": dict(kind="glow", n_in=1, nh=32, L=2, K=2, sp=(64, 64), gb=8, precision="fp16x3",
                  label="NetworkGlow(1,32,L=2,K=2) on 64x64x1"),
     # BASELINE configs[2] (amortized_glow_mnist_inpainting.jl:82-89 at the SURVEY 8d size)
-    "cfg3": dict(kind="cglow", n_in=1, n_cond=1, nh=32, L=2, K=10, sp=(64, 64), gb=128, precision="fp32",
+    "cfg3": dict(kind="cglow", n_in=1, n_cond=1, nh=32, L=2, K=10, sp=(64, 64), gb=128, precision="fp16x3",
                  label="NetworkConditionalGlow(1,1,32,L=2,K=10;split_scales=true) on 64x64x1 + 64x64x1 condition"),
     # BASELINE configs[3] (BASELINE does not fix L, K, n_hidden; the reference's default block k1 = k2 = 3)
     "cfg4": dict(kind="hint", n_in=2, nh=128, L=2, K=4, sp=(128, 128), gb=32, precision="bf16x3", k2=3,
                  label="NetworkMultiScaleHINT(2,128,L=2,K=4;split_scales=true,k1=3,k2=3) on 128x128x2"),
     # BASELINE configs[4] (L = K = 2, n_hidden = 32 unless told otherwise)
-    "cfg5": dict(kind="glow", n_in=1, nh=32, L=2, K=2, sp=(64, 64, 64), gb=8, precision="fp32",
+    "cfg5": dict(kind="glow", n_in=1, nh=32, L=2, K=2, sp=(64, 64, 64), gb=8, precision="fp16x3",
                  label="NetworkGlow3D(1,32,L=2,K=2) on 64x64x64x1"),
 }
 

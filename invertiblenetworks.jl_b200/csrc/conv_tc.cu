@@ -111,6 +111,19 @@ CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows
   return m;
 }
 
+CUtensorMap make_rows_map_u8(const void* base, int pitch, long long rows, int box_c, int box_rows, bool swizzle64) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, str, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(2, "cuTensorMapEncodeTiled(byte rows) failed with %d", (int)r);
+  return m;
+}
+
 // fp32 planes [nplanes][rows][cols], box (cols, box_rows, 1), no swizzle: the tap-row planes of the fused chain's Pq (a
 // ragged last tile is clipped at `rows`, so it cannot spill into the next plane)
 CUtensorMap make_planes_map_f32_dense(const float* base, int cols, long long rows, int nplanes, int box_rows) {

@@ -15,6 +15,10 @@ struct Planes {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
   int pitch;  // channels per row
+  // The lo plane holds ONE byte per value: the upper byte (sign, exponent, two mantissa bits) of the half-precision
+  // residual, rounded.  Only the hidden planes that k_rb_chain2 stores for k_wgrad2_tc use it (chain_planes_lo8):
+  // 3 instead of 4 bytes per stored value on the one tensor family that dominates the step's DRAM traffic.
+  int lo8 = 0;
 };
 
 // tile geometry of a P-pixel TMA box over (W,H,D,B); ok == false when the shape cannot be tiled
@@ -136,6 +140,8 @@ struct ChainSpec {
   CouplingFuse* fuse = nullptr;    // fold the affine coupling into the col2im (out0 etc. are then unused)
 };
 int chain_n3pad(int taps, int Cn);
+// the hidden planes a storing pass of the fused chain writes carry 1-byte lo planes (Planes::lo8) in this precision mode
+bool chain_planes_lo8(int prec);
 inline int chain_nh_pad(int nh) { return nh <= 128 ? 128 : 256; }  // hidden width the chain kernels run at
 int chain_kpad(int taps, int C, int extra);  // im2col width: taps*C (+ extra columns) rounded up to 64
 bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn);

@@ -50,6 +50,7 @@ struct ChainArgs {
   // taps*Cn to (taps/3)*cq columns per pixel (Pq[m][tg*cq + n], cq = Cn rounded up to 4, pitch nq = (taps/3)*cq)
   int qsum, Cn, cq, nq, ntg;
   int pstag_bytes;        // k_rb_chain2: size of the P staging area
+  int lo8;                // k_rb_chain2, store: the lo planes are written as one byte per value (Planes::lo8)
   int hints;              // k_rb_chain2 L2 eviction hints of the bulk stores: 1 hidden planes evict_first, 2 P / Pq evict_last
   int npiece, n3piece;    // k_rb_chain2: GEMM3 runs in npiece passes of n3piece (<= 256) columns through the same TMEM region
   int mode;               // 0: bias + ReLU (forward)   1: relu-grad masks (backward)
@@ -1343,8 +1344,17 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             for (int g = 0; g < 2; ++g) {
               const uint32_t off = (uint32_t)(((kk * 2 + g) ^ (row & 7)) << 4);
               *reinterpret_cast<uint4*>(dst + off) = make_uint4(wh[4 * g], wh[4 * g + 1], wh[4 * g + 2], wh[4 * g + 3]);
-              if (NT == 3)
+              if (NT == 3 && !a.lo8)
                 *reinterpret_cast<uint4*>(dst + kPlane + off) = make_uint4(wl[4 * g], wl[4 * g + 1], wl[4 * g + 2], wl[4 * g + 3]);
+            }
+            if (NT == 3 && a.lo8 && !(a.exp & 8)) {
+              // 16 residuals -> 16 bytes: the upper byte of each half, rounded to nearest (a carry out of the lower
+              // half-word only touches the last mantissa bit of its neighbour, which the truncation drops).  Rows of
+              // 64 bytes in the SWIZZLE_64B pattern of the byte plane's store: 16-byte chunk ^ ((row >> 1) & 3)
+              constexpr uint32_t R = 0x00800080u;
+              const uint4 o = make_uint4(__byte_perm(wl[0] + R, wl[1] + R, 0x7531), __byte_perm(wl[2] + R, wl[3] + R, 0x7531),
+                                         __byte_perm(wl[4] + R, wl[5] + R, 0x7531), __byte_perm(wl[6] + R, wl[7] + R, 0x7531));
+              *reinterpret_cast<uint4*>(stag + slot * SLOT + kPlane + row * 64 + ((kk ^ ((row >> 1) & 3)) << 4)) = o;
             }
             if (!(a.exp & 16)) fence_proxy_async();
             ++cs;
@@ -1473,6 +1483,7 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
             if (!(a.exp & 4)) {
 #pragma unroll
               for (int pl = 0; pl < NP; ++pl) {
+                // (with lo8 the second map is the byte plane: box of 64 bytes x 128 rows, same coordinates)
                 if (a.hints & 1)
                   tma_store_2d_hint(stg ? &maps.O2[pl] : &maps.O1[pl], stag + slot * SLOT + pl * kPlane, 64 * c, tile * 128, pol);
                 else
@@ -1913,6 +1924,17 @@ int chain_n3pad(int taps, int Cn) {
 
 int chain_kpad(int taps, int C, int extra) { return (taps * C + extra + 63) / 64 * 64; }
 
+// INB_PLANE_LO8=0 keeps 2-byte lo planes.  The single-CTA kernels (INB_CHAIN_KERNEL=t|smem, diagnostics) write 2-byte planes.
+bool chain_planes_lo8(int prec) {
+  static const bool on = [] {
+    const char* e = getenv("INB_PLANE_LO8");
+    const char* k = getenv("INB_CHAIN_KERNEL");
+    const char* sm = getenv("INB_CHAIN_SMEM");
+    return !(e && e[0] == '0') && !(k && (k[0] == 't' || k[0] == 's')) && !(sm && sm[0] == '1');
+  }();
+  return on && prec_f16(prec);  // the upper byte of an IEEE half is sign + exponent + 2 mantissa bits; of a bfloat16 it is not
+}
+
 bool chain_supported(const Geo& g, int B, int k1, int k2, int nh, int C_in, int Cn) {
   if (k2 != 1) return false;
   if (nh < 1 || nh > 256) return false;  // runs at 128 or 256 hidden channels (chain_nh_pad), smaller blocks zero padded
@@ -1969,6 +1991,11 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.npiece = (a.n3pad + 255) / 256;
   a.n3piece = a.n3pad / a.npiece;
   const bool pair = (a.n3pad % (16 * a.npiece) == 0) && force == 0;
+  if (a.store) {
+    INB_CHECK(s.o1.lo8 == s.o2.lo8, "fused ResidualBlock chain: both stored tensors must use the same lo-plane format");
+    INB_CHECK(!s.o1.lo8 || (pair && f16), "fused ResidualBlock chain: 1-byte lo planes need the CTA-pair kernel and fp16x3");
+    a.lo8 = s.o1.lo8;
+  }
   INB_CHECK(pair || (!f16 && a.n3pad <= 480), "fused ResidualBlock chain: %d expanded columns need the CTA-pair kernel", a.n3pad);
   static const bool no_qsum = [] { const char* e = getenv("INB_CHAIN_QSUM"); return e && e[0] == '0'; }();
   a.Cn = s.Cn;
@@ -1994,7 +2021,10 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     mp.W1[pl] = make_rows_map(pl ? s.w1.lo : s.w1.hi, s.in.pitch, s.nh, 64, wrows);
     mp.W2[pl] = make_rows_map(pl ? s.w2.lo : s.w2.hi, s.nh, s.nh, 64, wrows);
     mp.W3[pl] = make_rows_map(pl ? s.w3.lo : s.w3.hi, s.nh, a.n3pad, 64, w3rows);
-    if (a.store) {
+    if (a.store && pl == 1 && s.o1.lo8) {
+      mp.O1[1] = make_rows_map_u8(s.o1.lo, s.nh, a.M, 64, 128, true);
+      mp.O2[1] = make_rows_map_u8(s.o2.lo, s.nh, a.M, 64, 128, true);
+    } else if (a.store) {
       mp.O1[pl] = make_rows_map(pl ? s.o1.lo : s.o1.hi, s.nh, a.M, 64, 128);
       mp.O2[pl] = make_rows_map(pl ? s.o2.lo : s.o2.hi, s.nh, a.M, 64, 128);
     } else {

@@ -13,7 +13,8 @@
 // The four epilogue warps are idle during the main loop: they sum the columns of the P tile while it sits in shared
 // memory, which yields the bias gradient db[p] = sum_pix P[pix][p] (:157,164) without another pass over HBM.
 //
-// Warps: 0 TMA producer | 1 MMA issuer | 2..5 bias sums during the loop, TMEM -> dw afterwards.
+// Warps: 0 TMA producer | 1 MMA issuer | 2..5 expansion of 1-byte lo planes during the loop, TMEM -> dw afterwards |
+// 6..9 bias sums during the loop.
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 #include "tc_maps.cuh"
@@ -37,10 +38,12 @@ struct Wgrad2Args {
   uint32_t stage_bytes, p_plane, q_plane;  // per plane: P tile, Q tile (of the widest group)
   float* dbpart;    // [gridDim.x][np] partial bias sums, nullable
   int f16;          // operand planes are IEEE halves (INB_PREC_FP16X3)
+  int p8, q8;       // the lo plane of P / Q holds one byte per value (Planes::lo8): expanded to halves in shared memory
 };
 
+constexpr int kWg2Threads = 320;
 template <int NT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kWg2Threads, 1)
 k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUtensorMap mP1,
             const __grid_constant__ CUtensorMap mQ0, const __grid_constant__ CUtensorMap mQ1,
             const __grid_constant__ CUtensorMap mD, const Wgrad2Args a) {
@@ -50,7 +53,8 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_bytes);
   uint64_t* empty = full + 8;
   uint64_t* tfull = empty + 8;
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* conv = tfull + 1;   // [8] the 1-byte lo planes of a stage have been expanded (p8 / q8)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(conv + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.y;
   const int q0 = grp * 256;
@@ -65,7 +69,11 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, do_bias ? 1 + patoms : 1); }
+      for (int s = 0; s < a.stages; ++s) {
+        mbar_init(full + s, 1);
+        mbar_init(empty + s, do_bias ? 1 + patoms : 1);
+        mbar_init(conv + s, 4);
+      }
       mbar_init(tfull, 1);
       fence_barrier_init();
     }
@@ -82,7 +90,8 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint32_t tx = NP * (patoms + qatoms) * ATOM;
+      // a 1-byte lo plane arrives as ONE dense [32 pixels][np | nqg bytes] box at the start of the operand's lo region
+      const uint32_t tx = patoms * ATOM * (NP == 2 ? (a.p8 ? 3 : 4) : 2) / 2 + qatoms * ATOM * (NP == 2 ? (a.q8 ? 3 : 4) : 2) / 2;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.stages;
         mbar_wait(empty + s, ((kb / a.stages) & 1) ^ 1);
@@ -92,10 +101,14 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
         uint8_t* sq = sp + NP * a.p_plane;
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl) {
-          for (int at = 0; at < patoms; ++at)
-            tma_load_2d(pl ? &mP1 : &mP0, full + s, sp + pl * a.p_plane + at * ATOM, at * 64, row0);
-          for (int at = 0; at < qatoms; ++at)
-            tma_load_2d(pl ? &mQ1 : &mQ0, full + s, sq + pl * a.q_plane + at * ATOM, q0 + at * 64, row0);
+          if (pl && a.p8) tma_load_2d(&mP1, full + s, sp + a.p_plane, 0, row0);
+          else
+            for (int at = 0; at < patoms; ++at)
+              tma_load_2d(pl ? &mP1 : &mP0, full + s, sp + pl * a.p_plane + at * ATOM, at * 64, row0);
+          if (pl && a.q8) tma_load_2d(&mQ1, full + s, sq + a.q_plane, q0, row0);
+          else
+            for (int at = 0; at < qatoms; ++at)
+              tma_load_2d(pl ? &mQ1 : &mQ0, full + s, sq + pl * a.q_plane + at * ATOM, q0 + at * 64, row0);
         }
       }
     }
@@ -108,6 +121,7 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.stages;
         mbar_wait(full + s, (kb / a.stages) & 1);
+        if (a.p8 | a.q8) mbar_wait(conv + s, (kb / a.stages) & 1);
         tc_fence_after();
         const uint32_t sp = smem_u32(smem + (size_t)s * a.stage_bytes);
         const uint32_t sq = sp + NP * a.p_plane;
@@ -128,15 +142,16 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
       }
       umma_commit(tfull);
     }
-  } else {
-    const int ew = warp - 2;  // 0..3
-    if (do_bias && ew < patoms) {
-      // column sums of the P tile (atom ew = channels [64 ew, 64 ew + 64)): lane owns channels 2*lane, 2*lane+1
+  } else if (warp >= 6) {
+    // bias warps: column sums of the P tile (atom bw = channels [64 bw, 64 bw + 64)): lane owns channels 2*lane, 2*lane+1
+    const int bw = warp - 6;
+    if (do_bias && bw < patoms) {
       float s0 = 0.f, s1 = 0.f;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.stages;
         mbar_wait(full + s, (kb / a.stages) & 1);
-        const uint8_t* at = smem + (size_t)s * a.stage_bytes + ew * ATOM;
+        if (a.p8) mbar_wait(conv + s, (kb / a.stages) & 1);  // the lo halves of P exist once they have been expanded
+        const uint8_t* at = smem + (size_t)s * a.stage_bytes + bw * ATOM;
 #pragma unroll 8
         for (int px = 0; px < kWgPB; ++px) {
           const uint32_t off = px * 128 + ((((uint32_t)lane >> 2) ^ (px & 7)) << 4) + (lane & 3) * 4;
@@ -152,14 +167,57 @@ k_wgrad2_tc(const __grid_constant__ CUtensorMap mP0, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
       }
-      *reinterpret_cast<float2*>(a.dbpart + (long long)blockIdx.x * a.np + ew * 64 + 2 * lane) = make_float2(s0, s1);
+      *reinterpret_cast<float2*>(a.dbpart + (long long)blockIdx.x * a.np + bw * 64 + 2 * lane) = make_float2(s0, s1);
+    }
+    asm volatile("bar.sync 3, 256;" ::: "memory");  // the epilogue warps may now reuse the stages as their staging area
+  } else {
+    const int ew = warp - 2;  // 0..3
+    // 1-byte lo planes: ONE dense box [32 pixels][np (nqg) bytes] per operand lands at the start of the operand's lo
+    // region (the TMA unit is request-rate bound: a 256-byte row costs what a 64-byte one does).  Warp ew expands the
+    // 64 channels of atom ew (byte b of a value -> half b << 8): every lane reads its eight 8-byte pieces, the four
+    // warps synchronise (the box overlays the atoms of other warps), then each writes the eight 16-byte chunks of its
+    // MN-major SWIZZLE_128B atom, and the MMA warp is told through conv[s].
+    const bool conv_on = (a.p8 | a.q8) != 0;
+    const int j8 = lane & 7, rb = lane >> 3;
+    if (conv_on) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        mbar_wait(full + s, (kb / a.stages) & 1);
+        uint8_t* sp = smem + (size_t)s * a.stage_bytes;
+        uint8_t* pl8 = sp + a.p_plane;                     // [32][np] bytes
+        uint8_t* ql8 = sp + NP * a.p_plane + a.q_plane;    // [32][nqg] bytes
+        const bool dp = a.p8 && ew < patoms, dq = a.q8 && ew < qatoms;
+        uint2 srcp[8], srcq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (dp) srcp[i] = *reinterpret_cast<const uint2*>(pl8 + (rb + 4 * i) * a.np + ew * 64 + j8 * 8);
+          if (dq) srcq[i] = *reinterpret_cast<const uint2*>(ql8 + (rb + 4 * i) * nqg + ew * 64 + j8 * 8);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rb + 4 * i;
+          const uint32_t off = (uint32_t)(r * 128 + ((j8 ^ (r & 7)) << 4));
+          if (dp)
+            *reinterpret_cast<uint4*>(pl8 + ew * ATOM + off) =
+                make_uint4(__byte_perm(srcp[i].x, 0u, 0x1404), __byte_perm(srcp[i].x, 0u, 0x3424),
+                           __byte_perm(srcp[i].y, 0u, 0x1404), __byte_perm(srcp[i].y, 0u, 0x3424));
+          if (dq)
+            *reinterpret_cast<uint4*>(ql8 + ew * ATOM + off) =
+                make_uint4(__byte_perm(srcq[i].x, 0u, 0x1404), __byte_perm(srcq[i].x, 0u, 0x3424),
+                           __byte_perm(srcq[i].y, 0u, 0x1404), __byte_perm(srcq[i].y, 0u, 0x3424));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv + s);
+      }
     }
     {
       // partial tile -> scratch: the pipeline stages are free now and serve as the staging area of the TMA store
       // (SWIZZLE_128B boxes of 32 fp32 columns x 128 rows, as for P in the fused chain)
       mbar_wait(tfull, 0);
       tc_fence_after();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // every bias warp has finished reading the last stages
+      asm volatile("bar.sync 3, 256;" ::: "memory");  // every bias warp has finished reading the last stages
       const int q = warp & 3;  // TMEM lane quadrant
       const int row = q * 32 + lane;
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
@@ -283,6 +341,9 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   const int NP = NT == 1 ? 1 : 2;
   Wgrad2Args a{};
   a.f16 = prec_f16(c.prec) ? 1 : 0;
+  a.p8 = s.P.lo8;
+  a.q8 = s.Q.lo8;
+  INB_CHECK(!(a.p8 | a.q8) || (NT == 3 && a.f16), "tensor-core wgrad: 1-byte lo planes exist in fp16x3 only");
   a.M = s.M;
   a.nblocks = (int)cdiv(s.M, kWgPB);
   a.np = s.np;
@@ -311,20 +372,22 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   float* dbpart = c.ar->f32((size_t)gx * s.np);  // sized in the dry run too (gradient pointers are fake there)
   a.dbpart = s.db ? dbpart : nullptr;
   if (c.dry()) return 0;
-  const size_t smem = (size_t)stages * a.stage_bytes + 17 * 8 + 16;
+  const size_t smem = (size_t)stages * a.stage_bytes + 25 * 8 + 16;
   CUtensorMap mP0 = make_rows_map(s.P.hi, s.P.pitch, s.M, 64, kWgPB);
-  CUtensorMap mP1 = make_rows_map(s.P.lo, s.P.pitch, s.M, 64, kWgPB);
+  CUtensorMap mP1 = a.p8 ? make_rows_map_u8(s.P.lo, s.P.pitch, s.M, s.np, kWgPB, false) : make_rows_map(s.P.lo, s.P.pitch, s.M, 64, kWgPB);
   CUtensorMap mQ0 = make_rows_map(s.Q.hi, s.Q.pitch, s.M, 64, kWgPB);
-  CUtensorMap mQ1 = make_rows_map(s.Q.lo, s.Q.pitch, s.M, 64, kWgPB);
+  INB_CHECK(!a.q8 || a.qtot <= 256, "tensor-core wgrad: a 1-byte Q plane wider than 256 columns is not supported");
+  CUtensorMap mQ1 = a.q8 ? make_rows_map_u8(s.Q.lo, s.Q.pitch, s.M, nqmax, kWgPB, false) : make_rows_map(s.Q.lo, s.Q.pitch, s.M, 64, kWgPB);
   CUtensorMap mD = make_rows_map_f32(part, nqmax, (long long)ng * gx * s.np, 32, 128);
-  Prof pf(c, F_WGRAD_TC, 1, 2.0 * s.M * a.qtot * s.np * NT, 2.0 * NP * s.M * (s.np + a.qtot));
+  Prof pf(c, F_WGRAD_TC, 1, 2.0 * s.M * a.qtot * s.np * NT,
+          (double)s.M * (s.np * (NP == 2 ? (a.p8 ? 3.0 : 4.0) : 2.0) + a.qtot * (NP == 2 ? (a.q8 ? 3.0 : 4.0) : 2.0)));
   dim3 grid(gx, ng, 1);
   if (NT == 3) {
     INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad2_tc<3><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
+    k_wgrad2_tc<3><<<grid, kWg2Threads, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   } else {
     INB_CUDA(cudaFuncSetAttribute(k_wgrad2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_wgrad2_tc<1><<<grid, 192, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
+    k_wgrad2_tc<1><<<grid, kWg2Threads, smem, c.st>>>(mP0, mP1, mQ0, mQ1, mD, a);
   }
   INB_CUDA(cudaGetLastError());
   const int npr = s.np_real > 0 ? s.np_real : s.np;

@@ -228,6 +228,7 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
     op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, -1, h.xin);
     size_t m = c.ar->mark();
     Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
+    H1.lo8 = H2.lo8 = chain_planes_lo8(c.prec) ? 1 : 0;
     const int n3pad = chain_n3pad(T1, s.Cout);
     Planes W1, W2, W3;
     if (p.pre[0]) {  // packed by rb_prepack_chain before the scale's first flow step
@@ -294,6 +295,7 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     // dY3 -> dY2 -> dY1 -> dX in one fused kernel (conv_tc_chain.cu); dY2 / dY1 go to HBM for the weight
     // gradients, which read every hidden tensor exactly once and produce the bias gradients on the way
     Planes G1 = planes_new(c, M, nh);
+    H1.lo8 = H2.lo8 = G1.lo8 = G2.lo8 = chain_planes_lo8(c.prec) ? 1 : 0;  // as the storing passes wrote / write them
     const int kp = chain_kpad(T1, Cout, 0);
     const int n3pad = chain_n3pad(T1, Cin);
     Planes W3c, W2d, W1e;

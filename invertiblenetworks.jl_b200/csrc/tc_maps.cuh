@@ -12,6 +12,8 @@ CUtensorMap make_w_map(const __nv_bfloat16* base, int ktot, int rows, int ck);
 CUtensorMap make_rows_map(const __nv_bfloat16* base, int pitch, long long rows, int box_c, int box_rows);
 CUtensorMap make_rows_map_f32(const float* base, int pitch, long long rows, int box_c, int box_rows);
 CUtensorMap make_rows_map_f32_dense(const float* base, int pitch, long long rows, int box_c, int box_rows);
+// byte planes [rows][pitch] (the 1-byte lo planes), box (box_c bytes, box_rows rows); swizzle64: SWIZZLE_64B (box_c == 64)
+CUtensorMap make_rows_map_u8(const void* base, int pitch, long long rows, int box_c, int box_rows, bool swizzle64);
 // fp32 planes [nplanes][rows][cols] (dense, cols * 4 a multiple of 16), box (cols, box_rows, 1), no swizzle
 CUtensorMap make_planes_map_f32_dense(const float* base, int cols, long long rows, int nplanes, int box_rows);
 }  // namespace inb
