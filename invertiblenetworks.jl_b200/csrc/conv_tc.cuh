@@ -94,6 +94,10 @@ struct Wgrad2TcSpec {
   float* db;
   const uint32_t* smax = nullptr;  // INB_PREC_FP16X3: one operand carries the gradient scale; the reduction divides by it
   int np_real = 0;                 // rows of dw / db that exist (P padded with zero channels up to np); 0 = np
+  // >= 0: column `ones_col` of Q is 1.0 in every pixel row (a spare padding column of the im2col rows), so the
+  // contraction itself yields db[p] = sum_pix P[pix][p] as column ones_col of the gradient tile - no bias warps, no
+  // second read of the P tile from shared memory (the kernel is bound by shared-memory bandwidth where Q is narrow)
+  int ones_col = -1;
 };
 void op_wgrad2_tc(Ctx& c, const Wgrad2TcSpec& s);
 int wgrad_overlap_ctas();  // CTAs per weight-gradient kernel when they run under the next step's chain passes (0 = off)

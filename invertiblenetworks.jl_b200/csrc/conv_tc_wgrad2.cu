@@ -262,6 +262,7 @@ struct WgradReduceDesc {
   float* dw;
   const float* dbpart;
   float* db;
+  int ones_col;  // >= 0: db[p] = column ones_col of the summed gradient tile (group 0) instead of the dbpart sums
   const uint32_t* smax;  // INB_PREC_FP16X3: the sums carry the gradient scale derived from *smax
 };
 struct WgradReduceArgs {
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
   const int ncta = q.ncta, np = q.np, pitch = q.pitch, C = q.C, T = q.T;
   const int ncol = T * C;
   const int npr = q.np_real;
-  const long long total = (long long)npr * ncol, outs = total + (dbpart ? npr : 0);
+  const bool has_db = dbpart != nullptr || q.ones_col >= 0;
+  const long long total = (long long)npr * ncol, outs = total + (has_db ? npr : 0);
   float osc = 1.f;
   if (q.smax) { float sc; f16_scale_from_max(__ldg(q.smax), sc, osc); }
   const int sub = threadIdx.x >> 6;  // which quarter of the partials (a warp works on 32 consecutive outputs)
@@ -286,7 +288,10 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const WgradReduceArgs a) {
     if (i < outs) {
       const float* src;
       long long step;
-      if (i >= total) {
+      if (i >= total && q.ones_col >= 0) {
+        src = part + (i - total) * pitch + q.ones_col;
+        step = (long long)np * pitch;
+      } else if (i >= total) {
         src = dbpart + (i - total);
         step = np;
       } else {
@@ -370,7 +375,8 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   // scratch: partial tiles [ng][gx][np][nqmax] and partial bias sums [gx][np]
   float* part = c.ar->f32((size_t)ng * gx * s.np * nqmax);
   float* dbpart = c.ar->f32((size_t)gx * s.np);  // sized in the dry run too (gradient pointers are fake there)
-  a.dbpart = s.db ? dbpart : nullptr;
+  const int ones_col = (s.db && s.ones_col >= 0 && s.ones_col < std::min(a.qtot, 256) && s.ones_col >= s.T * s.C) ? s.ones_col : -1;
+  a.dbpart = (s.db && ones_col < 0) ? dbpart : nullptr;
   if (c.dry()) return 0;
   const size_t smem = (size_t)stages * a.stage_bytes + 25 * 8 + 16;
   CUtensorMap mP0 = make_rows_map(s.P.hi, s.P.pitch, s.M, 64, kWgPB);
@@ -391,7 +397,7 @@ static long long wgrad2_launch(Ctx& c, const Wgrad2TcSpec& s, WgradReduceDesc& r
   }
   INB_CUDA(cudaGetLastError());
   const int npr = s.np_real > 0 ? s.np_real : s.np;
-  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, npr, s.dw, a.dbpart, s.db, prec_f16(c.prec) ? s.smax : nullptr};
+  rd = WgradReduceDesc{part, (int)gx, s.np, nqmax, s.C, s.T, npr, s.dw, a.dbpart, s.db, ones_col, prec_f16(c.prec) ? s.smax : nullptr};
   return (long long)npr * s.T * s.C + (s.db ? npr : 0);
 }
 

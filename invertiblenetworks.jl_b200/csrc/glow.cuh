@@ -37,6 +37,7 @@ struct RBHidden {
   // tensor-core path: the same three buffers hold bf16 hi/lo planes [M][nh]; xin is the padded
   // bf16 copy of the block input made by rb_forward (lives in the caller's arena scope)
   Planes xin{nullptr, nullptr, 0};
+  int xin_ones = -1;  // fused chain: column of the im2col rows that holds 1.0 (the bias gradient rides on dW1), -1 = none
   // fused-chain path: relu-grad masks of Y1 / Y2 as bit planes [M][nh/32], written by the storing forward pass
   uint32_t* bm1 = nullptr;
   uint32_t* bm2 = nullptr;

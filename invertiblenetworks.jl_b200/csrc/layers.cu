@@ -225,7 +225,10 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
       h.bm1 = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes((size_t)M * (nh / 32) * 4));
       h.bm2 = reinterpret_cast<uint32_t*>(c.ar->alloc_bytes((size_t)M * (nh / 32) * 4));
     }
-    op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, -1, h.xin);
+    // a spare padding column of the rows carries 1.0: the W1 weight gradient then delivers db1 as well (its packed
+    // weight column is zero, so the forward contraction does not see it)
+    h.xin_ones = (T1 * Cin < kp) ? T1 * Cin : -1;
+    op_im2col_tc(c, s.g, s.B, s.k1, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, kp, h.xin_ones, h.xin);
     size_t m = c.ar->mark();
     Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
     H1.lo8 = H2.lo8 = chain_planes_lo8(c.prec) ? 1 : 0;
@@ -330,10 +333,11 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     cs.add = add; cs.add_bs = add_bs; cs.add_n = s.c0;
     cs.smax = smax;
     op_rb_chain(c, cs);
-    const Wgrad2TcSpec wg[3] = {
+    Wgrad2TcSpec wg[3] = {
         Wgrad2TcSpec{M, H2, nh, dcol, Cout, T1, gr.W3, nullptr, smax, s.nh},   // :152
         Wgrad2TcSpec{M, G2, nh, H1, s.nh, 1, gr.W2, gr.b2, smax, s.nh},         // :156-157 (columns beyond n_hidden dropped)
         Wgrad2TcSpec{M, G1, nh, h.xin, Cin, T1, gr.W1, gr.b1, smax, s.nh}};     // :163-164
+    wg[2].ones_col = h.xin_ones;
     op_wgrad2_tc_multi(c, wg, 3);
     c.ar->release(m);
     return;
