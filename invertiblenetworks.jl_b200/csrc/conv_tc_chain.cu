@@ -1749,6 +1749,98 @@ __global__ void __launch_bounds__(32 * J) k_col2im_coupling(const Col2imArgs a, 
     if ((threadIdx.x & 31) == 0 && gmax > 0.f) atomicMax(f.amax, __float_as_uint(gmax));
   }
 }
+// The same fused step with ONE THREAD PER PIXEL, for the 2-D tap-row planes of Pq (every plane is [M][cq] dense, so the
+// cq floats of consecutive pixels are contiguous: the warp's 16-byte loads cover whole lines, and with lanes along the
+// pixels every access to the (B, C, px) tensors X1 / Y1 / dY1 / dY3 is a full 128-byte line too).  No shared-memory
+// transpose, no block barrier, 3 * CN / 4 independent 16-byte loads in flight per thread (the two-phase kernel above
+// has 3 and is latency-bound at a third of the HBM rate).  Same order of additions and the same formulas: bit-identical
+// to k_col2im_coupling.  C1 = channels of the transformed half (CN = 2 C1 = cq columns per plane).
+template <int C1, int MODE>
+__global__ void __launch_bounds__(128) k_col2im_coupling_px(const Col2imArgs a, const CouplingFuse f) {
+  constexpr int CN = 2 * C1, NV = CN / 4;
+  __shared__ float red[4];
+  const int pix = (int)(blockIdx.x * 128 + threadIdx.x);
+  const long long b = blockIdx.y;
+  float lsum = 0.f, gmax = 0.f;
+  if (pix < (int)a.px) {
+    const long long m = b * a.px + pix;
+    const int y = (pix / a.W) % a.H;
+    const float* row = a.P + m * CN;
+    const long long rs = (long long)a.W * CN;
+    const bool up = y > 0, dn = y + 1 < a.H;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 w0[NV], w1[NV], w2[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) w1[v] = __ldg(reinterpret_cast<const float4*>(row + a.cstride) + v);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) w0[v] = up ? __ldg(reinterpret_cast<const float4*>(row - rs) + v) : zero;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) w2[v] = dn ? __ldg(reinterpret_cast<const float4*>(row + rs + 2 * a.cstride) + v) : zero;
+    float* ap = f.a1 + b * f.a1_bs + pix;
+    float* dp = (MODE == 2) ? f.d1 + b * f.d1_bs + pix : nullptr;
+    float av[C1], dv[C1];
+#pragma unroll
+    for (int ch = 0; ch < C1; ++ch) {
+      av[ch] = ap[(long long)ch * a.px];
+      if (MODE == 2) dv[ch] = dp[(long long)ch * a.px];
+    }
+    const float osc = col2im_scale(a);
+    float y3[CN];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      y3[4 * v] = ((w0[v].x + w1[v].x) + w2[v].x) * osc;
+      y3[4 * v + 1] = ((w0[v].y + w1[v].y) + w2[v].y) * osc;
+      y3[4 * v + 2] = ((w0[v].z + w1[v].z) + w2[v].z) * osc;
+      y3[4 * v + 3] = ((w0[v].w + w1[v].w) + w2[v].w) * osc;
+    }
+#pragma unroll
+    for (int ch = 0; ch < C1; ++ch) {
+      const float lsv = y3[ch], tvv = y3[C1 + ch];
+      const float S = cf_sigmoid(fmaxf(lsv, 0.f), f.low, f.high);  // RB output ReLU (layer_residual_block.jl:133)
+      const float T = fmaxf(tvv, 0.f);
+      if (MODE == 0) {
+        ap[(long long)ch * a.px] = S * av[ch] + T;       // invertible_layer_glow.jl:112
+        lsum += logf(fabsf(S));                          // :210
+      } else if (MODE == 1) {
+        ap[(long long)ch * a.px] = (av[ch] - T) / (S + 1.1920929e-07f);  // :127, eps(Float32)
+      } else {
+        const float dyv = dv[ch];
+        const float X1 = (av[ch] - T) / (S + 1.1920929e-07f);
+        float dS = dyv * X1;               // :144
+        dS -= f.invB / S;                  // :145-147, 211
+        ap[(long long)ch * a.px] = X1;
+        dp[(long long)ch * a.px] = dyv * S;  // :149
+        const float e = (f.high - S) / (S - f.low);  // activation_functions.jl:213-217 through the logit
+        const float dl = (f.high - f.low) * dS * e / ((1.f + e) * (1.f + e));
+        const float gl = (lsv < 0.f) ? 0.f : dl;  // _relugrad of the block's output ReLU (:84)
+        const float gt = (tvv < 0.f) ? 0.f : dyv; // dT = dY1 (:143)
+        f.dY3[(b * CN + ch) * a.px + pix] = gl;
+        f.dY3[(b * CN + C1 + ch) * a.px + pix] = gt;
+        gmax = fmaxf(gmax, fmaxf(fabsf(gl), fabsf(gt)));
+      }
+    }
+  }
+  if (MODE == 0 && f.ld) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) lsum += __shfl_xor_sync(0xFFFFFFFFu, lsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(f.ld, ((double)red[0] + (double)red[1] + (double)red[2] + (double)red[3]) * (double)f.invB);
+  }
+  if (MODE == 2 && f.amax) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+    if ((threadIdx.x & 31) == 0 && gmax > 0.f) atomicMax(f.amax, __float_as_uint(gmax));
+  }
+}
+template <int C1>
+static void launch_col2im_coupling_px(cudaStream_t st, const Col2imArgs& ca, const CouplingFuse& f, int B) {
+  const dim3 grid((unsigned)cdiv(ca.px, 128), (unsigned)B, 1);
+  if (f.mode == 0) k_col2im_coupling_px<C1, 0><<<grid, 128, 0, st>>>(ca, f);
+  else if (f.mode == 1) k_col2im_coupling_px<C1, 1><<<grid, 128, 0, st>>>(ca, f);
+  else k_col2im_coupling_px<C1, 2><<<grid, 128, 0, st>>>(ca, f);
+}
+
 template <int J>
 static void launch_col2im_coupling(cudaStream_t st, const dim3& grid, const Col2imArgs& ca, const CouplingFuse& f) {
   if (f.mode == 0) k_col2im_coupling<J, 0><<<grid, 32 * J, 0, st>>>(ca, f);
@@ -2108,6 +2200,18 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
       Prof pf(c, s.fuse->mode == 2 ? F_COUPLING_BWD : (s.fuse->mode == 1 ? F_COUPLING_INV : F_COUPLING_FWD), 1, 0,
               4.0 * prow * a.M + (s.fuse->mode == 2 ? 24.0 : 8.0) * elems);
       bool ok = true;
+      static const bool no_px = [] { const char* e = getenv("INB_COUPLING_PX"); return e && e[0] == '0'; }();
+      // thread-per-pixel variant: 2-D tap-row planes whose cq equals the 2 C1 channels of the block output
+      const bool px_ok = !no_px && a.qsum && s.g.D == 1 && ca.taps == 3 && ca.n3pad == s.Cn && (J == 1 || J == 2 || J == 3 || J == 4 || J == 6);
+      if (px_ok) {
+        switch (J) {
+          case 1: launch_col2im_coupling_px<2>(c.st, ca, *s.fuse, s.B); break;
+          case 2: launch_col2im_coupling_px<4>(c.st, ca, *s.fuse, s.B); break;
+          case 3: launch_col2im_coupling_px<6>(c.st, ca, *s.fuse, s.B); break;
+          case 4: launch_col2im_coupling_px<8>(c.st, ca, *s.fuse, s.B); break;
+          default: launch_col2im_coupling_px<12>(c.st, ca, *s.fuse, s.B); break;
+        }
+      } else
       switch (J) {
         case 1: launch_col2im_coupling<1>(c.st, grid, ca, *s.fuse); break;
         case 2: launch_col2im_coupling<2>(c.st, grid, ca, *s.fuse); break;
