@@ -1621,6 +1621,19 @@ __global__ void __launch_bounds__(32 * G) k_col2im_g(const Col2imArgs a) {
     const float4 w2 = (y + 1 < a.H) ? __ldg(reinterpret_cast<const float4*>(row + rs + 2 * a.cstride)) : zero;
     acc.x = (w0.x + w1.x) + w2.x; acc.y = (w0.y + w1.y) + w2.y;
     acc.z = (w0.z + w1.z) + w2.z; acc.w = (w0.w + w1.w) + w2.w;
+  } else if (!a.qsum && a.D == 1 && a.taps == 9) {
+    // full 3x3 P: nine independent loads, added in the rolled loop's order (a skipped tap adds +0)
+    const float* base = a.P + m * a.n3pad + 4 * g;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 w[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+      const bool ok = x + dx >= 0 && x + dx < a.W && y + dy >= 0 && y + dy < a.H;
+      w[tap] = ok ? __ldg(reinterpret_cast<const float4*>(base + (long long)(dx + dy * a.W) * a.n3pad + tap * a.cstride)) : zero;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) { acc.x += w[tap].x; acc.y += w[tap].y; acc.z += w[tap].z; acc.w += w[tap].w; }
   } else
   for (int tap = 0; tap < a.taps; ++tap) {
     int dx, dy, dz;
@@ -1681,6 +1694,19 @@ __global__ void __launch_bounds__(32 * J) k_col2im_coupling(const Col2imArgs a, 
       const float4 w2 = (y + 1 < a.H) ? __ldg(reinterpret_cast<const float4*>(row + rs + 2 * a.cstride)) : zero;
       acc.x = (w0.x + w1.x) + w2.x; acc.y = (w0.y + w1.y) + w2.y;
       acc.z = (w0.z + w1.z) + w2.z; acc.w = (w0.w + w1.w) + w2.w;
+    } else if (!a.qsum && a.D == 1 && a.taps == 9) {
+      // the full 3x3 P (GEMM3 wider than 128 columns): all nine loads in flight, added in the rolled loop's order
+      const float* base = a.P + m * a.n3pad + 4 * g;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 w[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+        const bool ok = x + dx >= 0 && x + dx < a.W && y + dy >= 0 && y + dy < a.H;
+        w[tap] = ok ? __ldg(reinterpret_cast<const float4*>(base + (long long)(dx + dy * a.W) * a.n3pad + tap * a.cstride)) : zero;
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) { acc.x += w[tap].x; acc.y += w[tap].y; acc.z += w[tap].z; acc.w += w[tap].w; }
     } else {
       for (int tap = 0; tap < a.taps; ++tap) {
         int dx, dy, dz;
