@@ -48,7 +48,8 @@ struct ChainArgs {
   int stages;
   // k_rb_chain2 with qsum: E3 sums the three horizontal taps of every (dy[,dz]) tap row on the SM, so P shrinks from
   // taps*Cn to (taps/3)*cq columns per pixel (Pq[m][tg*cq + n], cq = Cn rounded up to 4, pitch nq = (taps/3)*cq)
-  int qsum, Cn, cq, nq, ntg;
+  int qsum, Cn, cq, nq, ntg;   // qsum: 1 = whole tile staged at once (n3pad <= 128), 2 = one tap row at a time (<= 256)
+  int rpw;                // qsum == 2: row pitch (floats) of the per-tap-row staging: 32 * chunks + 4
   int pstag_bytes;        // k_rb_chain2: size of the P staging area
   int lo8;                // k_rb_chain2, store: the lo planes are written as one byte per value (Planes::lo8)
   int hints;              // k_rb_chain2 L2 eviction hints of the bulk stores: 1 hidden planes evict_first, 2 P / Pq evict_last
@@ -1392,7 +1393,53 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
       mbar_wait(d3f, (tl * a.npiece + pc) & 1);
       tc_fence_after();
       if (tr) tr[4] = clock64();
-      if (a.qsum) {
+      if (a.qsum == 2) {
+        // Wide GEMM3 (129..256 columns, 2-D): the same tap-row planes, one tap row at a time.  Round tg stages the aligned
+        // 32-column chunks that cover columns [3 tg Cn, 3 tg Cn + 3 Cn) of D3 as fp32 rows, sums the three horizontal
+        // taps into plane tg of the dense Q tile and frees the rows for the next round (the rows of a whole 224-column
+        // tile would not fit beside the ring).  Not deferred: the rows are reused.
+        if (tl > 0 && tid == 0) bulk_wait_read0();  // the previous tile's Pq store has read qst (the barrier below orders it)
+        const int ngrp = a.cq >> 2;
+        float* const qsw = raw + 128 * a.rpw;
+        for (int tg = 0; tg < a.ntg; ++tg) {
+          const int col0 = 3 * tg * a.Cn, cbase = col0 & ~31, o = col0 - cbase;
+          if (32 * kk < o + 3 * a.Cn) {
+            uint32_t r[32];
+            tmem_ld32(R0 + lane_sel + cbase + 32 * kk, r);
+            tmem_ld_wait();
+            float* dst = raw + row * a.rpw + 32 * kk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(dst + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+          tc_fence_before();
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+          const int nstep = a.rpw + a.Cn;
+#pragma unroll 1
+          for (int i = tid; i < 128 * ngrp; i += EPI) {
+            const int r = i & 127, g = i >> 7;
+            const int x = r & (a.W - 1);
+            const float* ctr = raw + r * a.rpw + o + a.Cn + 4 * g;
+            float4 acc = *reinterpret_cast<const float4*>(ctr);
+            if (x > 0) {
+              const float4 v = *reinterpret_cast<const float4*>(ctr - nstep);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (x + 1 < a.W) {
+              const float4 v = *reinterpret_cast<const float4*>(ctr + nstep);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            *reinterpret_cast<float4*>(qsw + (tg * 128 + r) * a.cq + 4 * g) = acc;
+          }
+          if (tg + 1 < a.ntg) asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");  // the rows may be overwritten
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory");
+        if (tid == 0) {
+          for (int tg = 0; tg < a.ntg; ++tg) tma_store_3d(&maps.P, qsw + tg * 128 * a.cq, 0, tile * 128, tg);
+          bulk_commit();
+        }
+      } else if (a.qsum) {
         // D3 rows -> plain fp32 rows in shared memory; then every (pixel, tap row, 4 channels) item adds its three
         // horizontal taps: Q[(y', x)][tg][n] = sum_dx D3[(y', x + dx)][(3 tg + dx + 1) Cn + n] (x + dx inside the image
         // row; a tile is whole image rows because 128 % W == 0); col2im then only sums over tap rows
@@ -2120,8 +2167,23 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   a.cq = (s.Cn + 3) / 4 * 4;
   a.ntg = taps / 3;
   a.nq = a.ntg * a.cq;
-  a.qsum = (pair && !no_qsum && taps >= 9 && 128 % s.g.W == 0 && (s.g.W & (s.g.W - 1)) == 0 && a.n3pad <= 128) ? 1 : 0;
+  const bool q_geo = pair && !no_qsum && taps >= 9 && 128 % s.g.W == 0 && (s.g.W & (s.g.W - 1)) == 0;
+  a.qsum = (q_geo && a.n3pad <= 128) ? 1 : 0;
   a.pstag_bytes = a.qsum ? (int)((((size_t)128 * (a.n3pad + 4) + (size_t)128 * a.nq) * 4 + 1023) / 1024 * 1024) : 4 * (int)kPlane;
+  static const bool no_qwide = [] { const char* e = getenv("INB_CHAIN_QWIDE"); return e && e[0] == '0'; }();
+  if (q_geo && !no_qwide && !a.qsum && taps == 9 && a.npiece == 1 && s.Cn % 4 == 0) {
+    // one tap row at a time: the aligned 32-column chunks covering 3 Cn columns at any of the three offsets
+    int nck = 0;
+    for (int tg = 0; tg < 3; ++tg) nck = std::max(nck, ((3 * tg * s.Cn) % 32 + 3 * s.Cn + 31) / 32);
+    const int rpw = 32 * nck + 4;
+    const int bytes = (int)((((size_t)128 * rpw + (size_t)128 * a.nq) * 4 + 1023) / 1024 * 1024);
+    const size_t fixed_w = (size_t)(a.store ? kChain2Slots * 2 : 0) * kPlane + bytes;
+    if (nck <= 4 && cap > aux + fixed_w && (cap - aux - fixed_w) / kPlane >= 4) {
+      a.qsum = 2;
+      a.rpw = rpw;
+      a.pstag_bytes = bytes;
+    }
+  }
   const bool tmem_a = a.n3pad <= 256 && force != 2;
   const size_t fixed = pair ? (size_t)(a.store ? kChain2Slots * 2 : 0) * kPlane + a.pstag_bytes
                             : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
