@@ -17,6 +17,7 @@ SWITCHES = [
     {"INB_GRAPHS": "0"},           # direct launches instead of CUDA-graph replay
     {"INB_L2_HINTS": "3"},         # L2 eviction hints on the bulk stores
     {"INB_CHAIN_QSUM": "0"},       # full tap-expanded P instead of the tap-row planes
+    {"INB_CHAIN_QWIDE": "0"},      # tap-row planes only where the whole tile can be staged at once (GEMM3 <= 128 columns)
 ]
 
 
