@@ -58,6 +58,10 @@ function sigmoid_bounds(act::ActivationFunction)
     (isapprox(y[1], (lo + hi) / 2; atol=1f-6) && isapprox(y[2], hi; atol=1f-6) && hi > lo) || return nothing
     return (lo, hi)
 end
+# channel counts the per-pixel kernels are instantiated for (csrc/elementwise.cu INB_FOR_C); a layer or network with any
+# other count (Conv1x1.k, invertible_layer_conv1x1.jl:42-49; ActNorm.k, invertible_layer_actnorm.jl:42-48) stays on the
+# reference
+const SUPPORTED_C = (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64)
 is_relu(act::ActivationFunction) = act.forward === ReLU                        # ReLUlayer(), :22-24
 # ShuffleLayer(; pattern) is a FUNCTION that returns Squeezer(x -> squeeze(x; pattern=pattern), ...)
 # (src/utils/dimensionality_operations.jl:12-19): the pattern is the closure's captured variable
@@ -74,7 +78,8 @@ function rb_on_b200(RB)
     return (k1 == 1 || k1 == 3) && (k2 == 1 || k2 == 3) && RB.pad[1] == (k1 - 1) ÷ 2 && RB.pad[2] == (k2 - 1) ÷ 2 &&
            RB.W1.data isa CuArray{Float32}
 end
-layer_on_b200(L::Union{CouplingLayerGlow,ConditionalLayerGlow}) = rb_on_b200(L.RB) && sigmoid_bounds(L.activation) !== nothing
+layer_on_b200(L::Union{CouplingLayerGlow,ConditionalLayerGlow}) =
+    rb_on_b200(L.RB) && sigmoid_bounds(L.activation) !== nothing && L.C.k in SUPPORTED_C
 # :uninit - every ActNorm still has s.data === nothing (the library runs the data-dependent initialisation),
 # :ready - all set, :mixed - a partially initialised network stays on the reference
 function actnorm_state(ANs)
@@ -87,6 +92,8 @@ all_actnorms(H::NetworkMultiScaleHINT) = vec(H.AN)
 function on_b200(G::Union{NetworkGlow,NetworkConditionalGlow})
     is_checkerboard(G.squeezer) || return false
     all(layer_on_b200, G.CL) || return false
+    all(L -> L.C.k in SUPPORTED_C, G.CL) || return false
+    all(AN -> AN.k in SUPPORTED_C, all_actnorms(G)) || return false
     b = sigmoid_bounds(G.CL[1, 1].activation)
     all(L -> sigmoid_bounds(L.activation) == b, G.CL) || return false
     all(AN -> !AN.is_reversed, all_actnorms(G)) || return false
@@ -324,7 +331,8 @@ bcs(X::CuArray{Float32,N}) where N = (Cint(size(X, N)), Cint(size(X, N - 1)), Cl
 
 # replaces src/layers/invertible_layer_actnorm.jl:60-77
 function forward(X::CuArray{Float32,N}, AN::ActNorm; logdet=nothing) where N
-    AN.is_reversed && return invoke(forward, Tuple{AbstractArray{Float32,N},ActNorm}, X, AN; logdet=logdet)
+    (AN.is_reversed || !(size(X, N - 1) in SUPPORTED_C)) &&
+        return invoke(forward, Tuple{AbstractArray{Float32,N},ActNorm}, X, AN; logdet=logdet)
     isnothing(logdet) ? logdet = (AN.logdet && ~AN.is_reversed) : logdet = logdet
     B, C, sp = bcs(X)
     if AN.s.data === nothing
@@ -342,7 +350,7 @@ end
 # replaces :80-97 (the logdet = true variant returns -logdet of the forward: left to the reference)
 function inverse(Y::CuArray{Float32,N}, AN::ActNorm; logdet=nothing) where N
     isnothing(logdet) ? logdet = (AN.logdet && AN.is_reversed) : logdet = logdet
-    (logdet || AN.is_reversed || AN.s.data === nothing) &&
+    (logdet || AN.is_reversed || AN.s.data === nothing || !(size(Y, N - 1) in SUPPORTED_C)) &&
         return invoke(inverse, Tuple{AbstractArray{Float32,N},ActNorm}, Y, AN; logdet=logdet)
     B, C, sp = bcs(Y)
     X = similar(Y)
@@ -354,7 +362,7 @@ end
 
 # replaces :100-123 (set_grad = true: grads overwritten, :113-114)
 function backward(ΔY::CuArray{Float32,N}, Y::CuArray{Float32,N}, AN::ActNorm; set_grad::Bool=true) where N
-    (set_grad && !AN.is_reversed) ||
+    (set_grad && !AN.is_reversed && size(Y, N - 1) in SUPPORTED_C) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},ActNorm}, ΔY, Y, AN; set_grad=set_grad)
     B, C, sp = bcs(Y)
     ΔX, X = similar(Y), similar(Y)
@@ -372,6 +380,7 @@ end
 # replaces src/layers/invertible_layer_conv1x1.jl:174-189 / 209-224 (logdet of an orthogonal map is 0)
 for (fn, sym) in ((:forward, :inb_conv1x1_forward), (:inverse, :inb_conv1x1_inverse))
     @eval function $fn(X::CuArray{Float32,N}, C::Conv1x1; logdet=nothing) where N
+        C.k in SUPPORTED_C || return invoke($fn, Tuple{AbstractArray{Float32,N},Conv1x1}, X, C; logdet=logdet)
         isnothing(logdet) ? logdet = C.logdet : logdet = logdet
         Y = similar(X)
         B, k, sp = bcs(X)
@@ -384,7 +393,7 @@ end
 
 # replaces :227-245: ΔX, X = C.inverse((ΔY, Y)) with the gradients w.r.t. v1, v2, v3 (accumulated unless cleared, :237-239)
 function inverse(Y_tuple::Tuple{CuArray{Float32,N},CuArray{Float32,N}}, C::Conv1x1; set_grad::Bool=true) where N
-    set_grad || return invoke(inverse, Tuple{Tuple,Conv1x1}, Y_tuple, C; set_grad=false)
+    (set_grad && C.k in SUPPORTED_C) || return invoke(inverse, Tuple{Tuple,Conv1x1}, Y_tuple, C; set_grad=set_grad)
     ΔY, Y = Y_tuple
     B, k, sp = bcs(Y)
     ΔX, X = similar(Y), similar(Y)
@@ -590,7 +599,8 @@ const HINT_PLANS = IdDict{Any,Tuple{Any,Ptr{Cvoid}}}()
 hint_precision(k2) = (PRECISION[] == 3 && k2 != 1) ? Cint(1) : PRECISION[]
 
 basic_on_b200(L::CouplingLayerBasic) = rb_on_b200(L.RB) && !L.is_reversed && sigmoid_bounds(L.activation) !== nothing
-hint_on_b200(H::CouplingLayerHINT) = !H.is_reversed && haskey(PERMUTE, H.permute) && all(basic_on_b200, H.CL)
+hint_on_b200(H::CouplingLayerHINT) = !H.is_reversed && haskey(PERMUTE, H.permute) && all(basic_on_b200, H.CL) &&
+                                     (H.C === nothing || H.C.k in SUPPORTED_C)
 hint_net_on_b200(H::NetworkMultiScaleHINT) = all(hint_on_b200, H.CL) && all(AN -> !AN.is_reversed, H.AN) &&
                                              actnorm_state(all_actnorms(H)) != :mixed
 
