@@ -209,7 +209,7 @@ end
 # ---------------------------------------------------------------- NetworkGlow
 # replaces src/networks/invertible_network_glow.jl:109-129
 function forward(X::CuArray{Float32,N}, G::NetworkGlow) where N
-    on_b200(G) || return invoke(forward, Tuple{AbstractArray{Float32,N},NetworkGlow}, X, G)
+    (on_b200(G) && N in (4, 5)) || return invoke(forward, Tuple{AbstractArray{Float32,N},NetworkGlow}, X, G)
     init = actnorm_state(all_actnorms(G)) == :uninit
     init && alloc_actnorms!(all_actnorms(G))
     st = plan_for(G, size(X), 0)
@@ -235,7 +235,7 @@ end
 
 # replaces :132-147
 function inverse(Z::CuArray{Float32,N}, G::NetworkGlow) where N
-    (on_b200(G) && actnorm_state(all_actnorms(G)) == :ready) ||
+    (on_b200(G) && actnorm_state(all_actnorms(G)) == :ready && length(input_shape(G, Z)) in (4, 5)) ||
         return invoke(inverse, Tuple{AbstractArray{Float32,N},NetworkGlow}, Z, G)
     Xshape = input_shape(G, Z)
     st = plan_for(G, Tuple(Xshape), 0)
@@ -249,7 +249,7 @@ end
 
 # replaces :150-191 (set_grad = true)
 function backward(ΔZ::CuArray{Float32,N}, Z::CuArray{Float32,N}, G::NetworkGlow; set_grad::Bool=true) where N
-    (set_grad && on_b200(G) && actnorm_state(all_actnorms(G)) == :ready) ||
+    (set_grad && on_b200(G) && actnorm_state(all_actnorms(G)) == :ready && length(input_shape(G, Z)) in (4, 5)) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},NetworkGlow},
                       ΔZ, Z, G; set_grad=set_grad)          # Jacobian paths stay on the reference
     Xshape = input_shape(G, Z)
@@ -269,7 +269,7 @@ end
 # ---------------------------------------------------------------- NetworkConditionalGlow
 # replaces src/networks/invertible_network_conditional_glow.jl:107-130
 function forward(X::CuArray{Float32,N}, C::CuArray{Float32,N}, G::NetworkConditionalGlow) where N
-    on_b200(G) || return invoke(forward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},NetworkConditionalGlow}, X, C, G)
+    (on_b200(G) && N in (4, 5)) || return invoke(forward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},NetworkConditionalGlow}, X, C, G)
     init = actnorm_state(all_actnorms(G)) == :uninit
     init && alloc_actnorms!(all_actnorms(G))
     st = plan_for(G, size(X), size(C, N - 1))
@@ -292,7 +292,7 @@ cond_channels(ZC, G::NetworkConditionalGlow, N) = size(ZC, N - 1) ÷ (G.split_sc
 
 # replaces :133-148
 function inverse(ZX::CuArray{Float32,N}, ZC::CuArray{Float32,N}, G::NetworkConditionalGlow) where N
-    (on_b200(G) && actnorm_state(all_actnorms(G)) == :ready) ||
+    (on_b200(G) && N in (4, 5) && actnorm_state(all_actnorms(G)) == :ready) ||
         return invoke(inverse, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},NetworkConditionalGlow}, ZX, ZC, G)
     st = plan_for(G, size(ZX), cond_channels(ZC, G, N))
     st.turn += 1
@@ -306,7 +306,7 @@ end
 # replaces :151-181
 function backward(ΔZX::CuArray{Float32,N}, ZX::CuArray{Float32,N}, ZC::CuArray{Float32,N},
                   G::NetworkConditionalGlow) where N
-    (on_b200(G) && actnorm_state(all_actnorms(G)) == :ready) ||
+    (on_b200(G) && N in (4, 5) && actnorm_state(all_actnorms(G)) == :ready) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},AbstractArray{Float32,N},NetworkConditionalGlow},
                       ΔZX, ZX, ZC, G)
     n_cond = cond_channels(ZC, G, N)
@@ -417,7 +417,7 @@ const RB_ARGT = (Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cin
 
 # replaces :119-134
 function forward(X1::CuArray{Float32,N}, RB::ResidualBlock; save=false) where N
-    (rb_on_b200(RB) && !save) || return invoke(forward, Tuple{AbstractArray{Float32,N},ResidualBlock}, X1, RB; save=save)
+    (rb_on_b200(RB) && N in (4, 5) && !save) || return invoke(forward, Tuple{AbstractArray{Float32,N},ResidualBlock}, X1, RB; save=save)
     Y = CUDA.zeros(Float32, size(X1)[1:N-2]..., size(RB.W3.data, N - 1), size(X1, N))
     check(ccall((:inb_resblock_forward, LIB), Cint,
                 (RB_ARGT..., Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cvoid}),
@@ -428,7 +428,7 @@ end
 
 # replaces :137-178 (set_grad = true: grads overwritten, :168-172)
 function backward(ΔX4::CuArray{Float32,N}, X1::CuArray{Float32,N}, RB::ResidualBlock; set_grad::Bool=true) where N
-    (rb_on_b200(RB) && set_grad) ||
+    (rb_on_b200(RB) && N in (4, 5) && set_grad) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},ResidualBlock}, ΔX4, X1, RB; set_grad=set_grad)
     ΔX1 = similar(X1)
     ps = (RB.W1, RB.W2, RB.W3, RB.b1, RB.b2)
@@ -490,35 +490,35 @@ end
 
 # replaces invertible_layer_glow.jl:104-117
 function forward(X::CuArray{Float32,N}, L::CouplingLayerGlow) where N
-    layer_on_b200(L) || return invoke(forward, Tuple{AbstractArray{Float32,N},CouplingLayerGlow}, X, L)
+    (layer_on_b200(L) && N in (4, 5)) || return invoke(forward, Tuple{AbstractArray{Float32,N},CouplingLayerGlow}, X, L)
     return cl_forward(X, nothing, L)
 end
 # replaces :120-133 (save = true hands the intermediates to the reference's own backward: left there)
 function inverse(Y::CuArray{Float32,N}, L::CouplingLayerGlow; save=false) where N
-    (layer_on_b200(L) && !save) || return invoke(inverse, Tuple{AbstractArray{Float32,N},CouplingLayerGlow}, Y, L; save=save)
+    (layer_on_b200(L) && N in (4, 5) && !save) || return invoke(inverse, Tuple{AbstractArray{Float32,N},CouplingLayerGlow}, Y, L; save=save)
     return cl_inverse(Y, nothing, L)
 end
 # replaces :136-170 (set_grad = true)
 function backward(ΔY::CuArray{Float32,N}, Y::CuArray{Float32,N}, L::CouplingLayerGlow; set_grad::Bool=true) where N
-    (layer_on_b200(L) && set_grad) ||
+    (layer_on_b200(L) && N in (4, 5) && set_grad) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},CouplingLayerGlow}, ΔY, Y, L; set_grad=set_grad)
     ΔX, X, _ = cl_backward(ΔY, Y, nothing, L)
     return ΔX, X
 end
 # replaces conditional_layer_glow.jl:94-112
 function forward(X::CuArray{Float32,N}, C::CuArray{Float32,N}, L::ConditionalLayerGlow) where N
-    layer_on_b200(L) || return invoke(forward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},ConditionalLayerGlow}, X, C, L)
+    (layer_on_b200(L) && N in (4, 5)) || return invoke(forward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},ConditionalLayerGlow}, X, C, L)
     return cl_forward(X, C, L)
 end
 # replaces :115-131
 function inverse(Y::CuArray{Float32,N}, C::CuArray{Float32,N}, L::ConditionalLayerGlow; save=false) where N
-    (layer_on_b200(L) && !save) ||
+    (layer_on_b200(L) && N in (4, 5) && !save) ||
         return invoke(inverse, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},ConditionalLayerGlow}, Y, C, L; save=save)
     return cl_inverse(Y, C, L)
 end
 # replaces :134-158
 function backward(ΔY::CuArray{Float32,N}, Y::CuArray{Float32,N}, C::CuArray{Float32,N}, L::ConditionalLayerGlow) where N
-    layer_on_b200(L) ||
+    (layer_on_b200(L) && N in (4, 5)) ||
         return invoke(backward, Tuple{AbstractArray{Float32,N},AbstractArray{Float32,N},AbstractArray{Float32,N},ConditionalLayerGlow}, ΔY, Y, C, L)
     return cl_backward(ΔY, Y, C, L)
 end
