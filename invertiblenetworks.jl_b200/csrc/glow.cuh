@@ -79,6 +79,9 @@ size_t rb_hidden_elems(const RBShape& s);
 // from the caller's arena scope, one launch per 24 blocks; returns false (and packs nothing) when the blocks do not run
 // on the fused chain.  The caller points RBParams::pre[direction] at out[i].
 bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int direction, PackedW* out);
+// the same for a block on the UNFUSED tensor-core convolutions (k2 = 3: the reference's default HINT block):
+// direction 0 = (W1 conv, W2 + I conv, W3 data), direction 1 = (W3 conv, W2 + I data, W1 data)
+bool rb_prepack_unfused(Ctx& c, const RBShape& s, const RBParams& prm, int direction, PackedW* out);
 
 // ActNorm -> CouplingLayerGlow forward: x -> y (y != x)
 void flow_forward(Ctx& c, const FlowShape& f, View x, View y, View cond, const FlowParams& p, double* ld);

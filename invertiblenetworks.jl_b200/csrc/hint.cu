@@ -99,8 +99,11 @@ static HintParams hint_prepack(Ctx& c, const HintShape& h, const HintParams& p, 
   store.resize(2 * n);
   for (int j = 0; j < n; ++j) {
     const RBShape rs = basic_rb(h, h.C >> (j + 1));
-    if (rb_prepack_chain(c, rs, &p.cl[j], 1, 0, &store[2 * j])) q.cl[j].pre[0] = &store[2 * j];
-    if (backward && rb_prepack_chain(c, rs, &p.cl[j], 1, 1, &store[2 * j + 1])) q.cl[j].pre[1] = &store[2 * j + 1];
+    if (rb_prepack_chain(c, rs, &p.cl[j], 1, 0, &store[2 * j]) || rb_prepack_unfused(c, rs, p.cl[j], 0, &store[2 * j]))
+      q.cl[j].pre[0] = &store[2 * j];
+    if (backward && (rb_prepack_chain(c, rs, &p.cl[j], 1, 1, &store[2 * j + 1]) ||
+                     rb_prepack_unfused(c, rs, p.cl[j], 1, &store[2 * j + 1])))
+      q.cl[j].pre[1] = &store[2 * j + 1];
   }
   return q;
 }

@@ -201,6 +201,28 @@ bool rb_prepack_chain(Ctx& c, const RBShape& s, const RBParams* prm, int n, int 
   return true;
 }
 
+bool rb_prepack_unfused(Ctx& c, const RBShape& s, const RBParams& p, int direction, PackedW* out) {
+  if (rb_path(c, s) != RB_PATH_UNFUSED) return false;
+  const int Cin = s.Cin(), T1 = s.T1(), T2 = s.T2(), nh = s.nh;
+  const int cin_pad = pad16(Cin), cout_pad = pad16(s.Cout);
+  if (direction == 0) {
+    out->w1 = planes_new(c, nh, T1 * cin_pad);
+    out->w2 = planes_new(c, nh, T2 * nh);
+    out->w3 = planes_new(c, cout_pad, T1 * nh);
+    op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, out->w1);
+    op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, out->w2, 1);  // + I: the skip of :125
+    op_pack_w_tc(c, PACK_DATA, nh, s.Cout, T1, p.W3, cout_pad, nh, out->w3);
+  } else {
+    out->w1 = planes_new(c, nh, T1 * cout_pad);
+    out->w2 = planes_new(c, nh, T2 * nh);
+    out->w3 = planes_new(c, cin_pad, T1 * nh);
+    op_pack_w_tc(c, PACK_CONV, nh, s.Cout, T1, p.W3, nh, cout_pad, out->w1);
+    op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, out->w2, 1);  // + I: the '+ dY2' of :155
+    op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, out->w3);
+  }
+  return true;
+}
+
 static ConvTcSpec tc_base(const RBShape& s) {
   ConvTcSpec cs{};
   cs.g = s.g;
@@ -259,10 +281,15 @@ static void rb_forward_tc(Ctx& c, const RBShape& s, View x2, View cond, const RB
   op_nchw_to_tc(c, s.g, s.B, x2.p, x2.bs, s.c0, cond.p, cond.bs, Cin, cin_pad, h.xin);
   size_t m = c.ar->mark();
   Planes H1 = planes_at(h.Y1, M, nh), H2 = planes_at(h.Y2, M, nh);
-  Planes W1 = planes_new(c, nh, T1 * cin_pad), W2 = planes_new(c, nh, T2 * nh), W3 = planes_new(c, cout_pad, T1 * nh);
-  op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
-  op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
-  op_pack_w_tc(c, PACK_DATA, nh, s.Cout, T1, p.W3, cout_pad, nh, W3);
+  Planes W1, W2, W3;
+  if (p.pre[0]) {  // packed once per pass (rb_prepack_unfused): a HINT coupling layer is visited many times
+    W1 = p.pre[0]->w1; W2 = p.pre[0]->w2; W3 = p.pre[0]->w3;
+  } else {
+    W1 = planes_new(c, nh, T1 * cin_pad); W2 = planes_new(c, nh, T2 * nh); W3 = planes_new(c, cout_pad, T1 * nh);
+    op_pack_w_tc(c, PACK_CONV, nh, Cin, T1, p.W1, nh, cin_pad, W1);
+    op_pack_w_tc(c, PACK_CONV, nh, nh, T2, p.W2, nh, nh, W2, 1);  // + I: the skip of :125
+    op_pack_w_tc(c, PACK_DATA, nh, s.Cout, T1, p.W3, cout_pad, nh, W3);
+  }
   {  // X2 = relu(conv(X, W1) + b1)                           layer_residual_block.jl:122-123
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k1; cs.in = h.xin; cs.cpad_in = cin_pad; cs.w = W1; cs.N = nh; cs.n_real = nh; cs.bias = p.b1;
@@ -349,8 +376,8 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
   Planes Wp = planes_new(c, std::max(nh, cin_pad), kmax);
   auto wview = [&](int rows, int k) { return planes_at(Wp.hi, rows, k); };
   {  // dY2 = relugrad(conv(dY3, W3), Y2)                        layer_residual_block.jl:151,154
-    Planes W = wview(nh, T1 * cout_pad);
-    op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W);
+    Planes W = p.pre[1] ? p.pre[1]->w1 : wview(nh, T1 * cout_pad);
+    if (!p.pre[1]) op_pack_w_tc(c, PACK_CONV, nh, Cout, T1, p.W3, nh, cout_pad, W);
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k1; cs.in = dY3p; cs.cpad_in = cout_pad; cs.w = W; cs.N = nh; cs.n_real = nh;
     cs.mode = 0; cs.out = G2; cs.mask = H2;
@@ -363,8 +390,8 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     op_wgrad_tc(c, ws);
   }
   {  // dY1 = relugrad(\nabla conv_data(dY2, W2) + dY2, Y1)      :155,161
-    Planes W = wview(nh, T2 * nh);
-    op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W, 1);  // + I: the '+ dY2' of :155
+    Planes W = p.pre[1] ? p.pre[1]->w2 : wview(nh, T2 * nh);
+    if (!p.pre[1]) op_pack_w_tc(c, PACK_DATA, nh, nh, T2, p.W2, nh, nh, W, 1);  // + I: the '+ dY2' of :155
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k2; cs.in = G2; cs.cpad_in = nh; cs.w = W; cs.N = nh; cs.n_real = nh;
     cs.mode = 0; cs.out = G1; cs.mask = H1;
@@ -378,8 +405,8 @@ static void rb_backward_tc(Ctx& c, const RBShape& s, const float* dY3, View x2, 
     op_colsum_tc(c, M, nh, G2, gr.b2);
   }
   {  // dX1 = \nabla conv_data(dY1, W1) (+ passthrough)          :162
-    Planes W = wview(cin_pad, T1 * nh);
-    op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, W);
+    Planes W = p.pre[1] ? p.pre[1]->w3 : wview(cin_pad, T1 * nh);
+    if (!p.pre[1]) op_pack_w_tc(c, PACK_DATA, nh, Cin, T1, p.W1, cin_pad, nh, W);
     ConvTcSpec cs = tc_base(s);
     cs.k = s.k1; cs.in = G1; cs.cpad_in = nh; cs.w = W; cs.N = cin_pad; cs.n_real = Cin;
     cs.mode = 1; cs.out0 = dx2.p; cs.out0_bs = dx2.bs; cs.n0 = s.c0;
