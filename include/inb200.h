@@ -43,7 +43,10 @@ extern "C" {
 #define INB_PREC_FP16X3 3      /* tcgen05 kind::f16 with IEEE-half operands, 3-term split: 2 x 11 significant bits per
                                   operand (float32-level products) at the bf16x3 rate; weights and gradients are
                                   pre-scaled by exact powers of two (the gradient scale is derived on the device from
-                                  max|dY| of each ResidualBlock backward).  Needs the fused chain (k2 = 1, n_hidden 128 / 256). */
+                                  max|dY| of each ResidualBlock backward).  Runs on the fused chain (k2 = 1, any n_hidden
+                                  <= 256, zero padded to 128 / 256); blocks with k2 = 3 compute in bf16x3.  The hidden
+                                  tensors handed to the weight gradients keep one byte of their lo half (14 significant
+                                  bits per stored value; the weight gradients stay at 4-7e-6 of the float64 result). */
 
 typedef struct inb_plan inb_plan;
 
