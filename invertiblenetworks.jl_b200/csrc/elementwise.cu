@@ -753,10 +753,26 @@ __device__ void hh_vgrad(const double* M, const double* v, double n, int C, doub
   __syncthreads();
 }
 
+// ActNorm's part of the same step (actnorm.jl:108-114,190), folded into this launch when `s` is given
+struct AnFinish {
+  const double* dsdb;
+  const float* s;
+  double px;
+  int logdet;
+  float *ds, *db;
+};
 __global__ void k_hh_grad_finish(const double* __restrict__ gram, const float* __restrict__ v1f,
                                  const float* __restrict__ v2f, const float* __restrict__ v3f, int C,
-                                 int freeze, float* dv1, float* dv2, float* dv3) {
+                                 int freeze, float* dv1, float* dv2, float* dv3, const AnFinish an) {
   extern __shared__ double dsm[];
+  if (an.s) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      float v = (float)an.dsdb[i];
+      if (an.logdet) v -= (float)an.px / an.s[i];  // actnorm.jl:108-110,190
+      an.ds[i] = v;
+      an.db[i] = (float)an.dsdb[C + i];
+    }
+  }
   if (freeze) {  // conv1x1.jl:132-134
     for (int i = threadIdx.x; i < C; i += blockDim.x) { dv1[i] = 0.f; dv2[i] = 0.f; dv3[i] = 0.f; }
     return;
@@ -795,16 +811,27 @@ __global__ void k_hh_grad_finish(const double* __restrict__ gram, const float* _
   hh_vgrad(M, v + 2 * C, n[2], C, tmp, dv3);
 }
 
-void op_hh_grad_finish(Ctx& c, int C, const double* gram, const float* v1, const float* v2,
-                       const float* v3, int freeze, float* dv1, float* dv2, float* dv3) {
-  if (c.dry()) return;
+static void launch_hh_grad_finish(Ctx& c, int C, const double* gram, const float* v1, const float* v2, const float* v3,
+                                  int freeze, float* dv1, float* dv2, float* dv3, const AnFinish& an) {
   Prof pf(c, F_GRAD_FINISH, 1, 0, 0);
   size_t sh = ((size_t)C * C + 3 * C + 2 * C + 2) * sizeof(double);
   INB_CHECK(sh <= 200 * 1024, "Conv1x1 with %d channels is not supported", C);
   if (sh > 48 * 1024)
     INB_CUDA(cudaFuncSetAttribute(k_hh_grad_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-  k_hh_grad_finish<<<1, 256, sh, c.st>>>(gram, v1, v2, v3, C, freeze, dv1, dv2, dv3);
+  k_hh_grad_finish<<<1, 256, sh, c.st>>>(gram, v1, v2, v3, C, freeze, dv1, dv2, dv3, an);
   INB_CUDA(cudaGetLastError());
+}
+void op_hh_grad_finish(Ctx& c, int C, const double* gram, const float* v1, const float* v2,
+                       const float* v3, int freeze, float* dv1, float* dv2, float* dv3) {
+  if (c.dry()) return;
+  launch_hh_grad_finish(c, C, gram, v1, v2, v3, freeze, dv1, dv2, dv3, AnFinish{nullptr, nullptr, 0.0, 0, nullptr, nullptr});
+}
+// the Householder and the ActNorm gradients of one flow step in ONE launch
+void op_hh_an_grad_finish(Ctx& c, int C, long long px, const double* gram, const float* v1, const float* v2, const float* v3,
+                          int freeze, float* dv1, float* dv2, float* dv3, const double* dsdb, const float* s, int logdet,
+                          float* ds, float* db) {
+  if (c.dry()) return;
+  launch_hh_grad_finish(c, C, gram, v1, v2, v3, freeze, dv1, dv2, dv3, AnFinish{dsdb, s, (double)px, logdet, ds, db});
 }
 
 __global__ void k_an_grad_finish(const double* __restrict__ dsdb, const float* __restrict__ s, int C,

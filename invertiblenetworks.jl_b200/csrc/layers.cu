@@ -518,8 +518,8 @@ void flow_backward(Ctx& c, const FlowShape& f, View dy, View y, View dx, View x,
     c.lane->fork(c.st);
     fc.st = c.lane->st;
   }
-  op_hh_grad_finish(fc, C, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3);
-  if (p.s) op_an_grad_finish(fc, C, px, dsdb, p.s, f.logdet, g.s, g.b);
+  if (p.s) op_hh_an_grad_finish(fc, C, px, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3, dsdb, p.s, f.logdet, g.s, g.b);
+  else op_hh_grad_finish(fc, C, gram, p.v1, p.v2, p.v3, f.freeze, g.v1, g.v2, g.v3);
   c.ar->release(m);
 }
 

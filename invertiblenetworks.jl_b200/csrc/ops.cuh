@@ -36,6 +36,9 @@ void op_hh_an_bwd(Ctx& c, long long px, int B, int C, View dy, View y, View dx, 
 // gram -> dv1,dv2,dv3 (conv1x1.jl:118-170 restructured); dsdb -> ds (- px/s when logdet), db
 void op_hh_grad_finish(Ctx& c, int C, const double* gram, const float* v1, const float* v2,
                        const float* v3, int freeze, float* dv1, float* dv2, float* dv3);
+void op_hh_an_grad_finish(Ctx& c, int C, long long px, const double* gram, const float* v1, const float* v2, const float* v3,
+                          int freeze, float* dv1, float* dv2, float* dv3, const double* dsdb, const float* s, int logdet,
+                          float* ds, float* db);
 void op_an_grad_finish(Ctx& c, int C, long long px, const double* dsdb, const float* s, int logdet,
                        float* ds, float* db);
 
