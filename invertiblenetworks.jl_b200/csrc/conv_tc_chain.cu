@@ -948,7 +948,8 @@ k_rb_chain2(const __grid_constant__ ChainMaps maps, const ChainArgs a) {
   constexpr int NP = (NT == 1) ? 1 : 2;
   constexpr uint32_t STAGE = kPlane;       // one ring granule (16 KB): a plane of an im2col block or of a GEMM3 weight
                                            // block, or both planes of a GEMM1 / GEMM2 weight half
-  constexpr uint32_t SLOT = 2 * kPlane;    // one staging slot: hi + lo planes of a 128 x 64 chunk
+  // one staging slot: hi + lo planes of a 128 x 64 chunk (16 + 16 KB), or hi + the 1-byte lo plane (16 + 8 KB)
+  const uint32_t SLOT = a.lo8 ? 3 * kPlane / 2 : 2 * kPlane;
   constexpr int EPI = kEpi2Warps * 32;
   // shared memory: [2 staging slots of the hidden-tensor stores (store mode only)][P staging][ring][barriers, biases]
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -2177,7 +2178,7 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     for (int tg = 0; tg < 3; ++tg) nck = std::max(nck, ((3 * tg * s.Cn) % 32 + 3 * s.Cn + 31) / 32);
     const int rpw = 32 * nck + 4;
     const int bytes = (int)((((size_t)128 * rpw + (size_t)128 * a.nq) * 4 + 1023) / 1024 * 1024);
-    const size_t fixed_w = (size_t)(a.store ? kChain2Slots * 2 : 0) * kPlane + bytes;
+    const size_t fixed_w = (size_t)(a.store ? kChain2Slots : 0) * (a.lo8 ? 3 * (size_t)kPlane / 2 : 2 * (size_t)kPlane) + bytes;
     if (nck <= 4 && cap > aux + fixed_w && (cap - aux - fixed_w) / kPlane >= 4) {
       a.qsum = 2;
       a.rpw = rpw;
@@ -2185,7 +2186,8 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
     }
   }
   const bool tmem_a = a.n3pad <= 256 && force != 2;
-  const size_t fixed = pair ? (size_t)(a.store ? kChain2Slots * 2 : 0) * kPlane + a.pstag_bytes
+  const size_t slot_bytes = a.lo8 ? 3 * (size_t)kPlane / 2 : 2 * (size_t)kPlane;
+  const size_t fixed = pair ? (size_t)(a.store ? kChain2Slots : 0) * slot_bytes + a.pstag_bytes
                             : (tmem_a ? (size_t)4 * kPlane : a.nchunk * chunk);
   // k_rb_chain2 runs its ring in 16 KB granules (up to 12 of them)
   int stages = (int)((cap - aux - fixed) / (pair ? (size_t)kPlane : stage));
