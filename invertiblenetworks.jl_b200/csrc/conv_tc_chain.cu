@@ -2192,6 +2192,10 @@ void op_rb_chain(Ctx& c, const ChainSpec& s) {
   // k_rb_chain2 runs its ring in 16 KB granules (up to 12 of them)
   int stages = (int)((cap - aux - fixed) / (pair ? (size_t)kPlane : stage));
   if (stages > (pair ? 12 : 8)) stages = pair ? 12 : 8;
+  if (const char* e = getenv("INB_CHAIN_MAXSTAGES")) {  // sensitivity studies: cap the ring depth
+    const int v = atoi(e);
+    if (v >= 4 && v < stages) stages = v;
+  }
   // the im2col block of GEMM1 stays resident while the weight blocks stream past it
   INB_CHECK(stages >= (pair ? 4 : 1 + s.nh / 128), "fused ResidualBlock chain: shared memory does not fit");
   a.stages = stages;
