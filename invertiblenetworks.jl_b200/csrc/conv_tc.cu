@@ -344,8 +344,8 @@ k_im2col9_tc(const float* __restrict__ in0, long long in0_bs, int W, int H, long
   unsigned char* tl = s_tile[wid][1];
 #pragma unroll
   for (int kb = 0; kb < KP; kb += 64) {
-    // small pixel counts (a batch shard of 8, the coarse scales): one 64-column block per grid row, so that the launch
-    // has KP / 64 times as many warps in flight (the kernel is latency-bound there)
+    // small pixel counts (a batch shard of 8 at the coarse scales: fewer than three blocks per SM): one 64-column block per
+    // grid row, so that the launch has KP / 64 times as many warps in flight (the kernel is latency-bound there)
     if (gridDim.y > 1 && kb / 64 != (int)blockIdx.y) continue;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -387,7 +387,8 @@ static void launch_im2col9(Ctx& c, const Geo& g, long long M, const float* in0, 
                            const uint32_t* smax, Planes out) {
   constexpr int KB = (9 * C + 63) / 64;
   const unsigned nb = (unsigned)cdiv(M, kI2cPix);
-  const dim3 grid(nb, (nb < 148u * 8u && KB > 1) ? KB : 1, 1);
+  // (measured: at 512 blocks the split already costs the 448-column kernel 7 us, at <= 256 blocks it halves its time)
+  const dim3 grid(nb, (nb < 148u * 3u && KB > 1) ? KB : 1, 1);
   k_im2col9_tc<C><<<grid, kI2cThreads, 0, c.st>>>(in0, in0_bs, g.W, g.H, g.px, M, ones_col,
                                                                      prec_f16(c.prec) ? 1 : 0, smax, out.hi, out.lo);
 }
